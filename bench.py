@@ -1,0 +1,520 @@
+#!/usr/bin/env python
+"""Benchmark of the APAP hot path on B200 (BASELINE.json metric: moving-DLT cells/s and mesh-warp
+Mpix/s vs roofline, beside the reference's CPU path timed on the same box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+One "step" = one pass of the hot path over one synthetic pair.  Two stages are timed, each for
+exactly K steps after W warm-up steps, on the device with CUDA events, with the L2 flushed (a
+256 MiB write) before every step:
+  * moving DLT  = K1 (weights + Gram contraction) + K2 (9x9 Jacobi + de-normalise)  -> cells/s
+    (the headline ``value``; ``ms_per_step`` is this stage)
+  * mesh warp   = K3 (`local_warp`), plus K4 blend and the fused warp+blend          -> Mpix/s
+    (reported under ``"warp"``)
+N = 1 runs BASELINE config c2 (4K pair, 5k keypoints, 200x200 grid).  N > 1 (under torchrun, one
+rank per GPU): every rank runs its own c2-shaped pair (independent pairs, no data-path collective,
+"scaling": "weak"), and the c3 pass (8K, 20k keypoints, 400x400) is additionally run strong-scaled
+-- cell rows and canvas row bands sharded, NCCL all-gather to assemble the panorama -- and
+reported under ``"c3_sharded"``.  Times are max over ranks.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "apap_moving_dlt_cells_per_s"
+UNIT = "cells/s"
+
+
+def _peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clock sampling
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed regions run."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for _, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [v for v in sm if mx and v > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baselines
+def _cpu_cells_worker(args):
+    name, seed, cells = args
+    from cvx_proj_b200 import synth
+    from oracle import apap_oracle as orc
+    sc = synth.make_scene(name, seed=seed)
+    t0 = time.perf_counter()
+    orc.local_homography_svd(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma, cells=cells)
+    return time.perf_counter() - t0
+
+
+def cpu_moving_dlt(name, n_cells, procs):
+    """The oracle's per-cell weighted-SVD loop (the reference's algorithm, pyviz/apap.py:147-168) on
+    ``n_cells`` evenly spread cells of the workload, split over ``procs`` worker processes."""
+    import multiprocessing as mp
+    from cvx_proj_b200 import synth
+    mesh = synth.CONFIGS[name]["mesh"]
+    pick = np.linspace(0, mesh * mesh - 1, n_cells).astype(np.int64)
+    cells = [(int(c // mesh), int(c % mesh)) for c in pick]
+    chunks = [cells[k::procs] for k in range(procs)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_cells_worker, [(name, 0, ch) for ch in chunks if ch])
+    wall = time.perf_counter() - t0
+    return n_cells / wall, wall
+
+
+def cpu_warp(name, n_rows):
+    """The oracle's vectorised float64 restatement of the pixel loop (pyviz/apap.py:206-215) on the
+    first ``n_rows`` canvas rows of the workload (single process, numpy)."""
+    from cvx_proj_b200 import synth
+    from oracle import apap_oracle as orc
+    sc = synth.make_scene(name)
+    img = sc.image(1)
+    sub = sc.vertices[::max(1, sc.mesh_cells // 8), ::max(1, sc.mesh_cells // 8)]
+    h_small = orc.local_homography_gram64(sc.src, sc.dst, sub, sc.gamma, sc.sigma)
+    reps = -(-sc.mesh_cells // h_small.shape[0])
+    h = np.repeat(np.repeat(h_small, reps, 0), reps, 1)[:sc.mesh_cells, :sc.mesh_cells].copy()
+    inv = orc.invert_grid(h)
+    n_rows = min(n_rows, sc.final_h)
+    t0 = time.perf_counter()
+    orc.local_warp(img, inv, sc.mesh, (sc.final_w, n_rows), (sc.offset_x, sc.offset_y))
+    wall = time.perf_counter() - t0
+    return sc.final_w * n_rows / wall / 1e6, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the path (oracle port: the reference is
+    pure Python and cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload or "c2"
+    procs = os.cpu_count() or 1
+    from cvx_proj_b200 import synth
+    cfg = synth.CONFIGS[name]
+    per_cell_s = 2.0e-3 * cfg["n_kp"] / 5000 + 3e-4
+    # bounded sample: ~2 s of wall per step on this box's cores
+    n_cells = int(min(cfg["mesh"] ** 2, max(4 * procs, 2.0 * procs / per_cell_s)))
+    times = []
+    for k in range(args.warmup + args.steps):
+        rate, wall = cpu_moving_dlt(name, n_cells, procs)
+        if k >= args.warmup:
+            times.append(wall)
+    ms = 1e3 * float(np.mean(times))
+    value = n_cells / (ms * 1e-3)
+    sample = (f"{n_cells} of {cfg['mesh'] ** 2} cells of {name} per step (evenly spread), oracle per-cell "
+              f"weighted SVD (cv.SVDecomp, float64) in {procs} worker processes")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": _workload_desc(name)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def _workload_desc(name):
+    from cvx_proj_b200 import synth
+    c = synth.CONFIGS[name]
+    return (f"{name}: synthetic {c['width']}x{c['height']} pair, {c['n_kp']} matched keypoints, "
+            f"APAP {c['mesh']}x{c['mesh']} grid, gamma=0.5 sigma=100")
+
+
+# ----------------------------------------------------------------------------------- our arm
+class Timer:
+    def __init__(self, torch):
+        self.torch = torch
+        self.pairs = []
+
+    def mark(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    @staticmethod
+    def ms(a, b):
+        return a.elapsed_time(b)
+
+
+class Pass:
+    """Device-resident state of one APAP pass (inputs already in HBM) + launch helpers."""
+
+    def __init__(self, torch, device, name, seed=0, rows=None):
+        from cvx_proj_b200 import synth
+        from cvx_proj_b200 import _runtime as rt
+        from cvx_proj_b200.apap import APAP, cell_lookup_tables
+        self.torch, self.device, self.rt = torch, device, rt
+        self.sc = sc = synth.make_scene(name, seed=seed)
+        self.st = APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y], device=device)
+        self.lib = rt.load_library()
+        m = sc.mesh_cells
+        self.row0, self.row1 = rows if rows is not None else (0, m)          # owned cell rows
+        verts = sc.vertices[self.row0:self.row1]
+        self.cells = verts.shape[0] * verts.shape[1]
+        table, tmats = self.st._prepare(sc.src, sc.dst)
+        self.n_pad = table.shape[0]
+        self.table = torch.from_numpy(table).to(device)
+        self.anchors = torch.from_numpy(verts.reshape(-1, 2).astype(np.float32)).to(device)
+        self.tmats = torch.from_numpy(tmats).to(device)
+        self.k_splits, self.cells_padded, nbytes = rt.gram_plan(self.cells, self.n_pad)
+        self.partials = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.h_out = torch.empty((self.cells, 9), dtype=torch.float32, device=device)
+        self.k2, self.g2 = (float(v) for v in self.st._kernel_scalars())
+        self.col_cell, self.row_cell = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, m, m)
+        self.stream = rt.stream_ptr(torch, device)
+
+    # -- moving DLT
+    def gram(self):
+        self.rt.check(self.lib.apap_gram_partials(self.table.data_ptr(), self.anchors.data_ptr(), 1, self.cells,
+                                                  self.n_pad, self.k2, self.g2, self.partials.data_ptr(),
+                                                  self.stream), "gram")
+
+    def eig(self):
+        self.rt.check(self.lib.apap_eig_denorm(self.partials.data_ptr(), self.tmats.data_ptr(), 1, self.cells,
+                                               self.n_pad, self.h_out.data_ptr(), None, self.stream), "eig")
+
+    # -- warp
+    def prepare_warp(self, px_rows=None):
+        """Upload the image, the inverted grid rows and the lookup tables (outside the timed region)."""
+        from cvx_proj_b200 import synth
+        from cvx_proj_b200.apap import build_hinv_rows
+        torch, sc = self.torch, self.sc
+        self.torch.cuda.synchronize()
+        m = sc.mesh_cells
+        h = np.tile(np.eye(3, dtype=np.float32), (m, m, 1, 1))
+        h[self.row0:self.row1] = self.h_out.cpu().numpy().reshape(-1, m, 3, 3)
+        inv = np.linalg.inv(h).astype(np.float32)
+        img = sc.image(1)
+        centre = synth.make_image(sc.width, sc.height, seed=2)
+        rows = build_hinv_rows(inv, self.col_cell, self.row_cell, sc.offset_x, sc.offset_y, sc.width, sc.height)
+        self.flagged_cells = float((rows[:, 9] >= 1).mean())
+        self.img = torch.from_numpy(img).to(self.device)
+        self.centre = torch.from_numpy(centre).to(self.device)
+        self.rows_dev = torch.from_numpy(rows).to(self.device)
+        self.col_dev = torch.from_numpy(self.col_cell).to(self.device)
+        self.row_dev = torch.from_numpy(self.row_cell).to(self.device)
+        self.px_rows = px_rows if px_rows is not None else (0, sc.final_h)
+        n = self.px_rows[1] - self.px_rows[0]
+        self.canvas = torch.empty((n, sc.final_w, 3), dtype=torch.uint8, device=self.device)
+        self.canvas2 = torch.empty_like(self.canvas)
+        self.pasted = torch.zeros_like(self.canvas)
+        self.host_img, self.host_centre = img, centre
+
+    def warp(self, fused=False):
+        self.st.warp_device(self.img, self.rows_dev, self.col_dev, self.row_dev, self.sc.mesh_cells,
+                            self.px_rows[0], self.px_rows[1], centre_dev=self.centre if fused else None,
+                            out=self.canvas)
+
+    def blend(self):
+        self.rt.blend_device(self.torch, self.canvas, self.pasted, out=self.canvas2)
+
+
+def timed_steps(torch, flush, warmup, steps, body, n_marks):
+    """Run ``body(mark)`` warmup+steps times; ``body`` calls ``mark()`` n_marks times.  Returns the
+    per-interval mean milliseconds over the timed steps (list of n_marks-1 floats)."""
+    all_marks = []
+    for k in range(warmup + steps):
+        flush.add_(1)                       # 256 MiB write: evicts the 126 MB L2
+        marks = []
+        body(lambda: marks.append(_ev(torch)))
+        if k >= warmup:
+            all_marks.append(marks)
+    torch.cuda.synchronize()
+    sums = [0.0] * (n_marks - 1)
+    for marks in all_marks:
+        for i in range(n_marks - 1):
+            sums[i] += marks[i].elapsed_time(marks[i + 1])
+    return [s / steps for s in sums]
+
+
+def _ev(torch):
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from cvx_proj_b200 import _runtime as rt
+    from cvx_proj_b200 import sharding, synth
+
+    peaks, peak_src = _peaks()
+    name = args.workload or "c2"
+    K, W = args.steps, max(args.warmup, 3)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=device)
+    launches = 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fp32_peak = rt.fp32_peak_tflops(device)
+    p = Pass(torch, device, name, seed=rank)
+    sc = p.sc
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- stage 1: moving DLT (K1 + K2) ---------------------------------------------------------
+    def dlt_body(mark):
+        mark(); p.gram(); mark(); p.eig(); mark()
+    barrier()
+    t_gram, t_eig = timed_steps(torch, flush, W, K, dlt_body, 3)
+    barrier()
+    launches += 2 * K
+    ms_dlt = max_over_ranks(t_gram + t_eig)
+    ms_gram = max_over_ranks(t_gram)
+    cells_total = p.cells * world
+    value = cells_total / (ms_dlt * 1e-3)
+
+    # ---- stage 2: mesh warp (K3), blend (K4), fused K3+K4 -------------------------------------
+    p.prepare_warp()
+    barrier()
+    (t_warp,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(False), mark()), 2)
+    (t_fused,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(True), mark()), 2)
+    (t_blend,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.blend(), mark()), 2)
+    barrier()
+    launches += 3 * K
+    ms_warp, ms_fused, ms_blend = (max_over_ranks(t) for t in (t_warp, t_fused, t_blend))
+    canvas_px = sc.canvas_px
+    src_px = sc.width * sc.height
+    warp_bytes = 3 * canvas_px + 3 * src_px                       # write canvas once + read source once
+    fused_bytes = 3 * canvas_px + 3 * src_px + 3 * src_px
+    blend_bytes = 9 * canvas_px
+    hbm = peaks["hbm_gbs"]
+
+    # ---- e2e through the public API: pinned host buffers in, host arrays out -------------------
+    src_pin = rt.pinned_empty(sc.src.shape, np.float32); src_pin[...] = sc.src
+    dst_pin = rt.pinned_empty(sc.dst.shape, np.float32); dst_pin[...] = sc.dst
+    img_pin = rt.pinned_empty(p.host_img.shape, np.uint8); img_pin[...] = p.host_img
+    st = p.st
+    e2e_dlt, e2e_warp = [], []
+    h_host = None
+    for k in range(W + K):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h_host, _ = st.local_homography(src_pin, dst_pin, sc.vertices)
+        t1 = time.perf_counter()
+        warped = st.local_warp(img_pin, h_host, sc.mesh)
+        t2 = time.perf_counter()
+        if k >= W:
+            e2e_dlt.append(t1 - t0)
+            e2e_warp.append(t2 - t1)
+    launches += 3 * K
+    e2e_dlt_s = max_over_ranks(float(np.mean(e2e_dlt)))
+    e2e_warp_s = max_over_ranks(float(np.mean(e2e_warp)))
+    h2d_dlt = p.n_pad * 28 * 4 + p.cells * 8 + 144
+    d2h_dlt = p.cells * 36
+    h2d_warp = 3 * src_px + p.cells * 48 + 2 * (sc.final_w + sc.final_h)
+    d2h_warp = 3 * canvas_px
+
+    # ---- c3 strong-scaled across ranks (cell rows + row bands, one all-gather) -----------------
+    c3 = None
+    if args.c3 and (world > 1 or args.c3 == "always"):
+        c3 = run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks, barrier)
+        launches += c3.pop("_launches")
+
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded samples of the same workload ---------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        n_cells = int(min(sc.n_cells, max(4 * procs, 12.0 / (2.5e-3 * sc.src.shape[0] / 5000 + 3e-4))))
+        rate, wall = cpu_moving_dlt(name, n_cells, procs)
+        wrate, wwall = cpu_warp(name, 256)
+        cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+               "sample": (f"{n_cells} of {sc.n_cells} cells of {name} (evenly spread), oracle per-cell weighted SVD "
+                          f"(cv.SVDecomp float64, the reference's algorithm) over {procs} processes, {wall:.1f} s wall"),
+               "warp": {"value": wrate, "unit": "Mpix/s", "cores": 1,
+                        "sample": f"first 256 canvas rows of {name}, oracle vectorised float64 numpy, {wwall:.1f} s"}}
+
+    gram_flops = 2.0 * 24 * p.n_pad * p.cells
+    achieved_tf = gram_flops / (ms_gram * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dlt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": _workload_desc(name), "per_rank": "one pair per GPU (independent pairs)",
+                   "l2": "flushed before every timed step (256 MiB write)", "cells": p.cells,
+                   "n_kp_padded": p.n_pad, "k_splits": p.k_splits, "canvas": [sc.final_w, sc.final_h]},
+        "roofline": {"kernel": "k_gram", "bound": "fp32_fma", "achieved": achieved_tf, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak, "traffic": None,
+                     "peak_source": "FP32 FFMA probe kernel timed in this run (not in MEASURED_PEAKS.json)",
+                     "algorithmic": "2*24*n_kp_padded*cells flop per launch (24 executed terms)",
+                     "ms": ms_gram, "eig_ms": ms_dlt - ms_gram},
+        "e2e": {"value": cells_total / e2e_dlt_s, "unit": UNIT, "h2d_bytes_per_step": h2d_dlt,
+                "d2h_bytes_per_step": d2h_dlt, "ms_per_step": e2e_dlt_s * 1e3,
+                "call": "APAP.local_homography(src, dst, vertices) with pinned numpy inputs, numpy H out"},
+        "warp": {
+            "metric": "apap_mesh_warp_mpix_per_s", "value": world * canvas_px / (ms_warp * 1e-3) / 1e6, "unit": "Mpix/s",
+            "ms_per_step": ms_warp, "dtype": "u8",
+            "roofline": {"kernel": "k_warp", "bound": "hbm", "achieved": warp_bytes / (ms_warp * 1e-3) / 1e9,
+                         "peak": hbm, "unit": "GB/s", "frac": warp_bytes / (ms_warp * 1e-3) / 1e9 / hbm,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic": "3*canvas_px + 3*src_px bytes per launch"},
+            "fused_warp_blend": {"ms_per_step": ms_fused, "mpix_per_s": canvas_px / (ms_fused * 1e-3) / 1e6,
+                                 "hbm_frac": fused_bytes / (ms_fused * 1e-3) / 1e9 / hbm},
+            "blend": {"ms_per_step": ms_blend, "mpix_per_s": canvas_px / (ms_blend * 1e-3) / 1e6,
+                      "hbm_frac": blend_bytes / (ms_blend * 1e-3) / 1e9 / hbm},
+            "e2e": {"value": world * canvas_px / e2e_warp_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_warp,
+                    "d2h_bytes_per_step": d2h_warp, "ms_per_step": e2e_warp_s * 1e3,
+                    "call": "APAP.local_warp(img, H, mesh) with a pinned numpy image, numpy canvas out "
+                            "(includes the host per-cell np.linalg.inv the reference also does)"},
+            "exact_path_cells_frac": p.flagged_cells,
+        },
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "gpu_launches": launches,
+    }
+    if c3 is not None:
+        line["c3_sharded"] = c3
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks, barrier):
+    """BASELINE config c3 split over the ranks: cell rows [m0, m1) and the canvas rows they own per
+    rank, keypoints and source image replicated, one NCCL all-gather of the row bands."""
+    from cvx_proj_b200 import sharding
+    from cvx_proj_b200.apap import cell_lookup_tables
+    from cvx_proj_b200 import synth
+    cfg = synth.CONFIGS["c3"]
+    sc0 = synth.make_scene("c3")
+    col, row = cell_lookup_tables(sc0.mesh, sc0.final_w, sc0.final_h, cfg["mesh"], cfg["mesh"])
+    shards = sharding.plan_shards(row, cfg["mesh"], world)
+    me = shards[rank]
+    p = Pass(torch, device, "c3", seed=0, rows=(me.cell_row0, me.cell_row1))
+
+    def dlt_body(mark):
+        mark(); p.gram(); mark(); p.eig(); mark()
+    barrier()
+    t_gram, t_eig = timed_steps(torch, flush, W, K, dlt_body, 3)
+    barrier()
+    p.prepare_warp(px_rows=(me.px_row0, me.px_row1))
+    barrier()
+    (t_warp,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(False), mark()), 2)
+    barrier()
+    t_gather = 0.0
+    if world > 1:
+        def gather_body(mark):
+            mark(); sharding.gather_bands(p.canvas, shards, sc0.final_w); mark()
+        (t_gather,) = timed_steps(torch, flush, W, K, gather_body, 2)
+        barrier()
+    ms_dlt = max_over_ranks(t_gram + t_eig)
+    ms_warp = max_over_ranks(t_warp)
+    ms_gather = max_over_ranks(t_gather)
+    return {"workload": _workload_desc("c3"), "scaling": "strong", "n_gpus": world,
+            "cells_per_s": sc0.n_cells / (ms_dlt * 1e-3), "dlt_ms": ms_dlt, "gram_ms": max_over_ranks(t_gram),
+            "warp_mpix_per_s": sc0.canvas_px / (ms_warp * 1e-3) / 1e6, "warp_ms": ms_warp,
+            "allgather_ms": ms_gather, "allgather_bytes": 3 * sc0.canvas_px,
+            "shard": "cell rows + canvas row bands per rank; keypoints and source image replicated",
+            "_launches": 3 * K}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="c1..c5 (default c2)")
+    ap.add_argument("--c3", default="multi", choices=["multi", "always", ""],
+                    help="run the c3 sharded pass: with N>1 (default), always, or never ('')")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,467 @@
+"""APAP (moving-DLT local homographies + mesh warp) on B200.
+
+Host-side mirror of the reference class ``APAP`` in ``pyviz/apap.py`` -- same constructor,
+same method names, argument meaning, return layout and side effects -- over the C ABI of
+``libapap_b200.so`` (``include/apap_b200.h``).  What runs where:
+
+  host (numpy, bit-identical to the reference, O(N) or O(cells)):
+      getNormalize2DPts / getConditionerFromPts / point_normalize / matrix_generate
+      (pyviz/apap.py:35-119), the per-cell ``np.linalg.inv`` of ``local_warp``
+      (pyviz/apap.py:201-203), the cell lookup tables (pyviz/apap.py:207,209)
+  GPU (hand-written sm_100a kernels, no CPU fallback):
+      K1 weights + Gram contraction, K2 9x9 Jacobi + de-normalisation
+      (pyviz/apap.py:147-168), K3 mesh warp (pyviz/apap.py:206-215),
+      K4 uniform_blend (pyviz/apap_utils.py:75-88), local_weight (pyviz/apap.py:150-153)
+
+Inputs and outputs are host numpy arrays by default, exactly like the reference; passing a
+CUDA ``torch`` tensor as the image keeps the result on the device (opt-in).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _runtime as rt
+from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW
+
+__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "expand_gram", "build_hinv_rows", "cell_lookup_tables"]
+
+_U = 2.0 ** -24          # float32 unit roundoff
+
+
+# ------------------------------------------------------------------------------ host helpers
+def build_kp_table(src_point: np.ndarray, dlt: np.ndarray) -> np.ndarray:
+    """Keypoint table of the Gram kernel: ``[N_padded, 28]`` float32.
+
+    Row i = the 24 distinct non-zero sums' per-keypoint terms, then the raw keypoint
+    (kx, ky) the weight is measured from, then 2 floats of padding (112 B, 16-B aligned).
+    With ``m = [x, y, 1]`` (conditioned source point) and ``(x', y')`` the conditioned target,
+    the Gram matrix of the two DLT rows (pyviz/apap.py:106-118) is
+    ``[[S, 0, -Sx], [0, S, -Sy], [-Sx, -Sy, Sr]]`` with ``S = m m^T``, ``Sx = x' m m^T``,
+    ``Sy = y' m m^T``, ``Sr = (x'^2 + y'^2) m m^T``; each symmetric 3x3 block is packed as
+    ``[xx, xy, x, yy, y, 1]``.  Products are formed in float64 from the reference's float32
+    DLT entries and rounded once.  Rows past N are zero (they add nothing to any sum).
+    """
+    n = src_point.shape[0]
+    a = dlt.astype(np.float64)
+    x, y = a[0::2, 0], a[0::2, 1]
+    xp, yp = -a[0::2, 8], -a[1::2, 8]
+    m = np.stack([x * x, x * y, x, y * y, y, np.ones_like(x)], axis=1)           # [N, 6]
+    n_pad = max(KP_CHUNK, (n + KP_CHUNK - 1) // KP_CHUNK * KP_CHUNK)
+    tab = np.zeros((n_pad, KP_ROW), dtype=np.float32)
+    tab[:n, 0:6] = m
+    tab[:n, 6:12] = xp[:, None] * m
+    tab[:n, 12:18] = yp[:, None] * m
+    tab[:n, 18:24] = (xp * xp + yp * yp)[:, None] * m
+    tab[:n, 24:26] = src_point
+    return tab
+
+
+_SYM3 = np.array([[0, 1, 2], [1, 3, 4], [2, 4, 5]])
+
+
+def expand_gram(sums: np.ndarray) -> np.ndarray:
+    """``[..., 24]`` packed sums -> ``[..., 9, 9]`` Gram matrix (host helper for tests)."""
+    s = np.asarray(sums, dtype=np.float64)
+    g = np.zeros(s.shape[:-1] + (9, 9))
+    blk = lambda k: s[..., k * 6 + _SYM3]                                          # noqa: E731
+    g[..., 0:3, 0:3] = blk(0)
+    g[..., 3:6, 3:6] = blk(0)
+    g[..., 0:3, 6:9] = -blk(1)
+    g[..., 6:9, 0:3] = -blk(1)
+    g[..., 3:6, 6:9] = -blk(2)
+    g[..., 6:9, 3:6] = -blk(2)
+    g[..., 6:9, 6:9] = blk(3)
+    return g
+
+
+def cell_lookup_tables(mesh: np.ndarray, final_w: int, final_h: int, grid_rows: int, grid_cols: int):
+    """``(col_cell[final_w], row_cell[final_h])`` uint16: the cell the reference picks per pixel.
+
+    ``np.where(k < edges)[0][0] - 1`` (pyviz/apap.py:207,209,210) == ``searchsorted(edges, k,
+    'right') - 1``; an index of -1 wraps to the last cell like the reference's negative
+    indexing; a pixel at or beyond the last edge makes the reference raise IndexError, so do we.
+    """
+    mesh_w, mesh_h = mesh
+    out = []
+    for edges, extent, ncell in ((mesh_w, final_w, grid_cols), (mesh_h, final_h, grid_rows)):
+        edges = np.asarray(edges)
+        idx = np.searchsorted(edges, np.arange(extent), side="right")
+        if extent and idx.max(initial=0) >= edges.shape[0]:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")   # the reference's np.where(...)[0][0]
+        idx = idx - 1
+        if extent and (idx.max(initial=0) >= ncell):
+            raise IndexError(f"index {int(idx.max())} is out of bounds for axis with size {ncell}")
+        out.append(np.mod(idx, ncell).astype(np.uint16))
+    return out[0], out[1]
+
+
+def build_hinv_rows(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndarray, off_x: int, off_y: int,
+                    src_w: int, src_h: int) -> np.ndarray:
+    """Per-cell rows of the warp kernel: ``[rows*cols, 12]`` float32 = 9 entries of H^-1,
+    ``eps_x``, ``eps_y``, pad.
+
+    ``eps`` is a rigorous bound on the absolute error of the kernel's float32 source coordinate
+    inside the cell's pixel rectangle (two fused multiply-adds per numerator, reciprocal +
+    residual-corrected quotient).  A coordinate farther than eps from every integer gets the same
+    floor and bounds decision in float32 as in the reference's float64; the kernel recomputes the
+    others in float64.  ``eps = 1`` sends the whole cell to the float64 path (denominator changes
+    sign or comes close to zero inside the cell).
+    """
+    gr, gc = inv_h.shape[0], inv_h.shape[1]
+    h = inv_h.astype(np.float64).reshape(gr, gc, 9)
+
+    def extent(lut, n):      # per cell index: smallest / largest pixel coordinate mapped to it
+        lo = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+        hi = np.full(n, np.iinfo(np.int64).min, dtype=np.int64)
+        k = np.arange(lut.shape[0], dtype=np.int64)
+        np.minimum.at(lo, lut, k)
+        np.maximum.at(hi, lut, k)
+        return lo, hi
+
+    jlo, jhi = extent(col_cell.astype(np.int64), gc)
+    ilo, ihi = extent(row_cell.astype(np.int64), gr)
+    used = (jlo <= jhi)[None, :] & (ilo <= ihi)[:, None]
+    xlo = np.where(jlo <= jhi, jlo - off_x, 0).astype(np.float64)[None, :]
+    xhi = np.where(jlo <= jhi, jhi - off_x, 0).astype(np.float64)[None, :]
+    ylo = np.where(ilo <= ihi, ilo - off_y, 0).astype(np.float64)[:, None]
+    yhi = np.where(ilo <= ihi, ihi - off_y, 0).astype(np.float64)[:, None]
+    xa = np.maximum(np.abs(xlo), np.abs(xhi))
+    ya = np.maximum(np.abs(ylo), np.abs(yhi))
+    ah = np.abs(h)
+    m0 = ah[..., 0] * xa + ah[..., 1] * ya + ah[..., 2]
+    m1 = ah[..., 3] * xa + ah[..., 4] * ya + ah[..., 5]
+    m2 = ah[..., 6] * xa + ah[..., 7] * ya + ah[..., 8]
+    corners = np.stack([h[..., 6] * cx + h[..., 7] * cy + h[..., 8]
+                        for cx in (xlo, xhi) for cy in (ylo, yhi)], axis=-1)
+    same_sign = (corners > 0).all(axis=-1) | (corners < 0).all(axis=-1)
+    t2min = np.abs(corners).min(axis=-1) - 4 * _U * m2            # computed |t2| is at least this
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        ok = same_sign & (t2min > 0) & used
+        t2s = np.where(ok, t2min, 1.0)
+        eps = []
+        for mk, lim in ((m0, src_w + 2.0), (m1, src_h + 2.0)):
+            q = np.minimum(mk / t2s, lim)
+            e = 1.5 * ((2 * _U * mk + q * 2 * _U * m2) / t2s + 1.01 * _U * q) + 4e-6
+            eps.append(np.where(ok & np.isfinite(e) & (e < 0.25), e, 1.0))
+    rows = np.zeros((gr, gc, HINV_ROW), dtype=np.float32)
+    rows[..., 0:9] = inv_h.reshape(gr, gc, 9)
+    # round the bounds up when narrowing to float32
+    rows[..., 9] = np.nextafter(eps[0].astype(np.float32), np.float32(2))
+    rows[..., 10] = np.nextafter(eps[1].astype(np.float32), np.float32(2))
+    return rows.reshape(gr * gc, HINV_ROW)
+
+
+class LazyLocalWeight:
+    """The second return value of ``local_homography``: ``[mesh_n, pt_size, N]`` float64 weights
+    (pyviz/apap.py:144,153,169).
+
+    The reference materialises it eagerly although its driver never reads it
+    (pyviz/apap.py:242); at the benchmark configurations it is 40 MB ... 34 GB, so here it is
+    computed on the GPU on first access (``np.asarray(w)``, ``w[i, j]``, ``w[i]``), slice by slice.
+    """
+
+    def __init__(self, src_point, vertices, gamma, sigma, device=None):
+        self._src = np.ascontiguousarray(src_point, dtype=np.float32)
+        self._vert = np.ascontiguousarray(vertices, dtype=np.float64)
+        self._gamma = float(gamma)
+        self._inv = 1.0 / (sigma ** 2)
+        self._device = device
+        self.shape = (vertices.shape[0], vertices.shape[1], src_point.shape[0])
+        self.dtype = np.dtype(np.float64)
+        self.ndim = 3
+
+    def __len__(self):
+        return self.shape[0]
+
+    def rows(self, r0: int, r1: int) -> np.ndarray:
+        """Weights of the cell rows ``[r0, r1)`` as a host array ``[r1-r0, pt_size, N]``."""
+        torch, device = rt.torch_cuda(self._device)
+        lib = rt.load_library()
+        p, n = self.shape[1], self.shape[2]
+        out = np.empty((r1 - r0, p, n), dtype=np.float64)
+        if out.size == 0:
+            return out
+        kp = rt.to_device(torch, device, self._src)
+        per_call = max(1, min(65535 // max(p, 1), max(1, (1 << 28) // max(p * n * 8, 1))))   # <= 256 MB slices
+        with torch.cuda.device(device):
+            for a in range(r0, r1, per_call):
+                b = min(r1, a + per_call)
+                anchors = rt.to_device(torch, device, self._vert[a:b].reshape(-1, 2))
+                buf = torch.empty(((b - a) * p, n), dtype=torch.float64, device=device)
+                rt.check(lib.apap_local_weight(anchors.data_ptr(), kp.data_ptr(), (b - a) * p, n, self._inv,
+                                               self._gamma, buf.data_ptr(), rt.stream_ptr(torch, device)),
+                         "apap_local_weight")
+                out[a - r0:b - r0] = rt.to_host(torch, buf).reshape(b - a, p, n)
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        full = self.rows(0, self.shape[0])
+        return full if dtype is None else full.astype(dtype, copy=False)
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) >= 1 and isinstance(key[0], (int, np.integer)):
+            i = int(key[0]) % self.shape[0]
+            return self.rows(i, i + 1)[0][key[1:]] if len(key) > 1 else self.rows(i, i + 1)[0]
+        if isinstance(key, (int, np.integer)):
+            i = int(key) % self.shape[0]
+            return self.rows(i, i + 1)[0]
+        if isinstance(key, slice):
+            r0, r1, step = key.indices(self.shape[0])
+            if step == 1:
+                return self.rows(r0, r1)
+        return np.asarray(self)[key]
+
+
+# ------------------------------------------------------------------------------------ the class
+class APAP:
+    """Drop-in for the reference ``APAP`` (pyviz/apap.py:21-217)."""
+
+    def __init__(self, gamma, sigma, final_size, offset, device=None):
+        """``final_size = [width, height]`` of the stitched canvas, ``offset = [off_x, off_y]``
+        (pyviz/apap.py:22-32).  ``device`` (extension) selects the CUDA device."""
+        self.gamma = gamma
+        self.sigma = sigma
+        self.final_width, self.final_height = final_size
+        self.offset_x, self.offset_y = offset
+        self.device = device
+        self._lut_cache = {}
+
+    # ---- O(N) host pieces, numerically identical to the reference ------------------------------
+    @staticmethod
+    def getNormalize2DPts(point):
+        """Hartley normaliser: centroid to the origin, mean distance sqrt(2).
+        Returns ``(t[3,3] float32, normalised points [N,2])`` (pyviz/apap.py:35-59)."""
+        count = point.shape[0]
+        centre = np.mean(point, axis=0)
+        shifted = point - centre
+        mean_dist = np.mean(np.sqrt(np.sum(np.square(shifted), axis=1)))
+        scale = np.sqrt(2) / (mean_dist + 1e-8)
+        t = np.array([[scale, 0, -scale * centre[0]],
+                      [0, scale, -scale * centre[1]],
+                      [0, 0, 1]], dtype=np.float32)
+        homog = np.column_stack((np.array(point, copy=True), np.ones(count, dtype=np.float32)))
+        return t, t.dot(homog.T).T[:, :2]
+
+    @staticmethod
+    def getConditionerFromPts(point):
+        """Per-axis conditioner from the unbiased standard deviation (pyviz/apap.py:63-89)."""
+        count = point.shape[0]
+        mu_x, mu_y = np.mean(point, axis=0)
+        dev = np.std(point, axis=0)
+        dev = np.sqrt(dev * dev * count / (count - 1))
+        dev_x, dev_y = dev
+        dev_x = dev_x + (dev_x == 0)
+        dev_y = dev_y + (dev_y == 0)
+        kx = np.sqrt(2) / dev_x
+        ky = np.sqrt(2) / dev_y
+        return np.array([[kx, 0, (-kx * mu_x)],
+                         [0, ky, (-ky * mu_y)],
+                         [0, 0, 1]], dtype=np.float32)
+
+    @staticmethod
+    def point_normalize(nf, c):
+        """``cf = nf * diag(c) + translation(c)`` in float32 (pyviz/apap.py:92-100), vectorised;
+        element-wise multiply-then-add is the same two roundings as the reference's loop."""
+        cf = np.zeros_like(nf)
+        cf[:, 0] = nf[:, 0] * c[0, 0] + c[0, 2]
+        cf[:, 1] = nf[:, 1] * c[1, 1] + c[1, 2]
+        return cf
+
+    @staticmethod
+    def matrix_generate(sample_n, cf1, cf2):
+        """The ``[2N, 9]`` float32 DLT matrix (pyviz/apap.py:103-119), vectorised."""
+        dlt = np.zeros([sample_n * 2, 9], dtype=np.float32)
+        even, odd = dlt[0::2], dlt[1::2]
+        even[:, 0:2] = cf1[:sample_n]
+        even[:, 2] = 1
+        even[:, 6] = (-cf2[:sample_n, 0]) * cf1[:sample_n, 0]
+        even[:, 7] = (-cf2[:sample_n, 0]) * cf1[:sample_n, 1]
+        even[:, 8] = -cf2[:sample_n, 0]
+        odd[:, 3:5] = cf1[:sample_n]
+        odd[:, 5] = 1
+        odd[:, 6] = (-cf2[:sample_n, 1]) * cf1[:sample_n, 0]
+        odd[:, 7] = (-cf2[:sample_n, 1]) * cf1[:sample_n, 1]
+        odd[:, 8] = -cf2[:sample_n, 1]
+        return dlt
+
+    @staticmethod
+    def warp_coordinate_estimate(pt, homography):
+        """``homography @ pt`` divided by its third component (pyviz/apap.py:172-184)."""
+        target = homography @ pt
+        target /= target[2]
+        return target
+
+    # ---- moving DLT ----------------------------------------------------------------------------
+    def _prepare(self, src_point, dst_point):
+        """Host prologue of ``local_homography`` (pyviz/apap.py:129-145): normalise, condition,
+        build the DLT matrix; then pack the kernel inputs."""
+        src_point = np.asarray(src_point)
+        dst_point = np.asarray(dst_point)
+        sample_n, _ = src_point.shape
+        n1, nf1 = self.getNormalize2DPts(src_point)
+        n2, nf2 = self.getNormalize2DPts(dst_point)
+        c1 = self.getConditionerFromPts(nf1)
+        c2 = self.getConditionerFromPts(nf2)
+        cf1 = self.point_normalize(nf1, c1)
+        cf2 = self.point_normalize(nf2, c2)
+        dlt = self.matrix_generate(sample_n, cf1, cf2)
+        table = build_kp_table(src_point.astype(np.float32, copy=False), dlt)
+        # h -> inv(N2) (inv(C2) h C1) N1   (pyviz/apap.py:165-166); inverses in float32 like the reference
+        t2inv = np.linalg.inv(n2).astype(np.float64) @ np.linalg.inv(c2).astype(np.float64)
+        t1 = c1.astype(np.float64) @ n1.astype(np.float64)
+        tmats = np.concatenate([t2inv.reshape(9), t1.reshape(9)])
+        return table, tmats
+
+    def _upload_scene(self, torch, device, tables, anchors, tmats):
+        """One host->device copy for all kernel inputs of ``batch`` scenes: the three arrays are
+        packed into a pinned staging buffer (kept per instance) and sliced on the device.
+        Layout: float32 tables [b, n_pad, 28] | float32 anchors [b, cells, 2] | float64 tmats [b, 18]
+        (every section starts 16-byte aligned)."""
+        sizes = [tables.nbytes, anchors.nbytes, tmats.nbytes]
+        offs = [0, (sizes[0] + 15) // 16 * 16]
+        offs.append((offs[1] + sizes[1] + 15) // 16 * 16)
+        total = offs[2] + sizes[2]
+        stage = getattr(self, "_stage", None)
+        if stage is None or stage.numel() < total or stage.device != torch.device("cpu"):
+            stage = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self._stage = stage
+        host = stage.numpy()
+        for arr, off, nb in zip((tables, anchors, tmats), offs, sizes):
+            host[off:off + nb] = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        dev = stage[:total].to(device, non_blocking=True)
+        t_dev = dev[offs[0]:offs[0] + sizes[0]].view(torch.float32).view(tables.shape)
+        a_dev = dev[offs[1]:offs[1] + sizes[1]].view(torch.float32).view(anchors.shape)
+        m_dev = dev[offs[2]:offs[2] + sizes[2]].view(torch.float64).view(tmats.shape)
+        return t_dev, a_dev, m_dev
+
+    def _kernel_scalars(self):
+        k2 = -2.0 * math.log2(math.e) / (float(self.sigma) ** 2)
+        return np.float32(k2), np.float32(float(self.gamma) ** 2)
+
+    def local_homography_device(self, table_dev, anchors_dev, tmats_dev, batch, cells, out_h=None, partials=None,
+                                sweeps=None):
+        """Device-resident K1 + K2 (no host traffic): tensors in, ``[batch, cells, 9]`` float32 out."""
+        torch, device = rt.torch_cuda(table_dev.device)
+        lib = rt.load_library()
+        n_pad = table_dev.shape[-2]
+        _, _, nbytes = rt.gram_plan(cells, n_pad)
+        if partials is None:
+            partials = torch.empty(batch * nbytes // 4, dtype=torch.float32, device=device)
+        if out_h is None:
+            out_h = torch.empty((batch, cells, 9), dtype=torch.float32, device=device)
+        k2, g2 = self._kernel_scalars()
+        with torch.cuda.device(device):
+            rt.check(lib.apap_local_homography(
+                table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
+                float(k2), float(g2), partials.data_ptr(), out_h.data_ptr(),
+                sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
+                "apap_local_homography")
+        return out_h
+
+    def local_homography(self, src_point, dst_point, vertices):
+        """Local homography per mesh cell (pyviz/apap.py:121-169).
+
+        ``src_point``, ``dst_point``: ``[N, 2]``; ``vertices``: ``[mesh_n, pt_size, 2]`` (x, y).
+        Returns ``(H[mesh_n, pt_size, 3, 3] float32, local_weight[mesh_n, pt_size, N] float64)``;
+        the weights are a lazy array (see ``LazyLocalWeight``).
+        """
+        sample_n, _ = np.shape(src_point)
+        mesh_n, pt_size, _ = np.shape(vertices)
+        table, tmats = self._prepare(src_point, dst_point)
+        torch, device = rt.torch_cuda(self.device)
+        cells = mesh_n * pt_size
+        anchors = np.asarray(vertices, dtype=np.float64).reshape(cells, 2).astype(np.float32)
+        t_dev, a_dev, m_dev = self._upload_scene(torch, device, table[None], anchors[None], tmats[None])
+        h_dev = self.local_homography_device(t_dev, a_dev, m_dev, 1, cells)
+        h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
+        weight = LazyLocalWeight(np.asarray(src_point), np.asarray(vertices), self.gamma, self.sigma, self.device)
+        return h, weight
+
+    def local_homography_batch(self, src_points, dst_points, vertices):
+        """Extension (no reference API; its multi-image mode is a shell loop, run_all.sh:15,29):
+        several pairs in one launch.  ``vertices`` is one ``[mesh_n, pt_size, 2]`` array shared by
+        all pairs or a list of them (same shape).  Each item equals the single-pair call."""
+        count = len(src_points)
+        verts = vertices if isinstance(vertices, (list, tuple)) else [vertices] * count
+        mesh_n, pt_size, _ = np.shape(verts[0])
+        cells = mesh_n * pt_size
+        prepared = [self._prepare(s, d) for s, d in zip(src_points, dst_points)]
+        n_pad = max(t.shape[0] for t, _ in prepared)
+        tables = np.zeros((count, n_pad, KP_ROW), dtype=np.float32)
+        for k, (t, _) in enumerate(prepared):
+            tables[k, :t.shape[0]] = t
+        tmats = np.stack([m for _, m in prepared])
+        anchors = np.stack([np.asarray(v, dtype=np.float64).reshape(cells, 2).astype(np.float32) for v in verts])
+        torch, device = rt.torch_cuda(self.device)
+        t_dev, a_dev, m_dev = self._upload_scene(torch, device, tables, anchors, tmats)
+        h_dev = self.local_homography_device(t_dev, a_dev, m_dev, count, cells)
+        h = rt.to_host(torch, h_dev).reshape(count, mesh_n, pt_size, 3, 3)
+        return [h[k] for k in range(count)]
+
+    # ---- mesh warp -----------------------------------------------------------------------------
+    def _luts(self, mesh, grid_rows, grid_cols):
+        mesh = np.asarray(mesh)
+        key = (mesh.shape, mesh.tobytes(), int(self.final_width), int(self.final_height), grid_rows, grid_cols)
+        hit = self._lut_cache.get(key)
+        if hit is None:
+            hit = cell_lookup_tables(mesh, int(self.final_width), int(self.final_height), grid_rows, grid_cols)
+            self._lut_cache = {key: hit}
+        return hit
+
+    def warp_device(self, src_dev, rows_dev, col_dev, row_dev, grid_cols, row0=0, row1=None, centre_dev=None,
+                    out=None, force_exact=False):
+        """Device-resident K3 (optionally fused with K4): writes canvas rows ``[row0, row1)`` into
+        ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None)."""
+        torch, device = rt.torch_cuda(src_dev.device)
+        lib = rt.load_library()
+        fw, fh = int(self.final_width), int(self.final_height)
+        row1 = fh if row1 is None else row1
+        if out is None:
+            out = torch.empty((row1 - row0, fw, 3), dtype=torch.uint8, device=device)
+        ch, cw = (centre_dev.shape[0], centre_dev.shape[1]) if centre_dev is not None else (0, 0)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_warp(
+                src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], rows_dev.data_ptr(), col_dev.data_ptr(),
+                row_dev.data_ptr(), grid_cols, fw, fh, int(self.offset_x), int(self.offset_y), row0, row1,
+                centre_dev.data_ptr() if centre_dev is not None else None, ch, cw, out.data_ptr(),
+                1 if force_exact else 0, rt.stream_ptr(torch, device)), "apap_warp")
+        return out
+
+    def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False):
+        mesh_n, pt_size, _, _ = local_homography.shape
+        ori_h, ori_w, _ = ori_img.shape
+        # in-place per-cell inverse, stored back in the caller's array (pyviz/apap.py:201-203)
+        local_homography[...] = np.linalg.inv(local_homography)
+        col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
+        rows = build_hinv_rows(local_homography, col_cell, row_cell, int(self.offset_x), int(self.offset_y),
+                               int(ori_w), int(ori_h))
+        on_device = not isinstance(ori_img, np.ndarray)
+        torch, device = rt.torch_cuda(ori_img.device if on_device else self.device)
+        src_dev = ori_img.contiguous() if on_device else rt.to_device(torch, device, ori_img.astype(np.uint8, copy=False))
+        centre_dev = None
+        if centre_img is not None:
+            centre_dev = (centre_img.contiguous() if not isinstance(centre_img, np.ndarray)
+                          else rt.to_device(torch, device, centre_img.astype(np.uint8, copy=False)))
+        out = self.warp_device(src_dev, rt.to_device(torch, device, rows), rt.to_device(torch, device, col_cell),
+                               rt.to_device(torch, device, row_cell), pt_size, centre_dev=centre_dev,
+                               force_exact=force_exact)
+        return out if on_device else rt.to_host(torch, out)
+
+    def local_warp(self, ori_img, local_homography, mesh, progress=False):
+        """Warp ``ori_img`` onto the canvas through the per-cell homographies (pyviz/apap.py:186-217).
+
+        Like the reference it inverts ``local_homography`` IN PLACE (the caller's array holds the
+        inverses afterwards).  ``mesh`` is the ``[2, mesh_n+1]`` edge array of ``get_mesh``.
+        ``progress`` is accepted for compatibility (the reference's tqdm bar) and ignored.
+        Returns the ``[final_height, final_width, 3]`` uint8 canvas, zero where nothing maps.
+        """
+        return self._warp(ori_img, local_homography, mesh)
+
+    def local_warp_blend(self, ori_img, local_homography, mesh, centre_img):
+        """Extension: the reference driver's commented pipeline (pyviz/apap.py:258-261) in one
+        kernel -- warp, paste ``centre_img`` at the offsets, ``uniform_blend``.  Same in-place
+        inversion side effect as ``local_warp``."""
+        return self._warp(ori_img, local_homography, mesh, centre_img=centre_img)

@@ -1,0 +1,114 @@
+// extern "C" entry points of libapap_b200.so (declared in include/apap_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace apap {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char *msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int check_cuda(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (int)e;
+}
+
+static int check_table(const void *kp_table, const void *anchors, int batch, int cells, int n_kp_padded) {
+  if (!kp_table || !anchors) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || cells <= 0 || n_kp_padded <= 0) return fail(APAP_E_BADARG, "batch, cells and n_kp_padded must be > 0");
+  if (n_kp_padded % kChunk) return fail(APAP_E_BADARG, "n_kp_padded must be a multiple of APAP_KP_CHUNK");
+  if (reinterpret_cast<uintptr_t>(kp_table) & 15u) return fail(APAP_E_ALIGN, "kp_table must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(anchors) & 7u) return fail(APAP_E_ALIGN, "anchors must be 8-byte aligned");
+  return 0;
+}
+
+}  // namespace apap
+
+using namespace apap;
+
+extern "C" {
+
+int apap_abi_version(void) { return APAP_ABI_VERSION; }
+const char *apap_last_error(void) { return g_err; }
+
+int apap_device_sm_count(int *sm_count) {
+  if (!sm_count) return fail(APAP_E_BADARG, "null pointer");
+  int dev = 0, n = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  rc = check_cuda(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+  if (rc) return rc;
+  *sm_count = n;
+  return 0;
+}
+
+int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded, size_t *partial_bytes_per_scene) {
+  if (cells <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "gram_plan: bad sizes");
+  // the layout (k_splits, cells_padded) does not depend on the SM count; only the register tile does
+  const GramPlan p = make_gram_plan(cells, n_kp_padded, 148);
+  if (k_splits) *k_splits = p.k_splits;
+  if (cells_padded) *cells_padded = p.cells_padded;
+  if (partial_bytes_per_scene) *partial_bytes_per_scene = (size_t)p.k_splits * kTerms * p.cells_padded * sizeof(float);
+  return 0;
+}
+
+int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
+                       float neg2_log2e_inv_sigma_sq, float gamma_sq, float *partials, void *stream) {
+  int rc = check_table(kp_table, anchors, batch, cells, n_kp_padded);
+  if (rc) return rc;
+  if (!partials) return fail(APAP_E_BADARG, "null partials");
+  return launch_gram(kp_table, anchors, batch, cells, n_kp_padded, neg2_log2e_inv_sigma_sq, gamma_sq, partials,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded, float *out_h,
+                    int *out_sweeps, void *stream) {
+  if (!partials || !tmats || !out_h) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || cells <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "eig: bad sizes");
+  return launch_eig(partials, tmats, batch, cells, n_kp_padded, out_h, out_sweeps, static_cast<cudaStream_t>(stream));
+}
+
+int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats, int batch, int cells,
+                          int n_kp_padded, float neg2_log2e_inv_sigma_sq, float gamma_sq, float *partials,
+                          float *out_h, int *out_sweeps, void *stream) {
+  int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, neg2_log2e_inv_sigma_sq, gamma_sq,
+                              partials, stream);
+  if (rc) return rc;
+  return apap_eig_denorm(partials, tmats, batch, cells, n_kp_padded, out_h, out_sweeps, stream);
+}
+
+int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
+                      double gamma, double *out, void *stream) {
+  if (!anchors || !kp_xy || !out) return fail(APAP_E_BADARG, "null pointer");
+  if (cells < 0 || n_kp < 0) return fail(APAP_E_BADARG, "local_weight: negative size");
+  return launch_weight(anchors, kp_xy, cells, n_kp, inv_sigma_sq, gamma, out, static_cast<cudaStream_t>(stream));
+}
+
+int apap_warp(const uint8_t *src, int src_h, int src_w, const float *hinv, const uint16_t *col_cell,
+              const uint16_t *row_cell, int grid_cols, int canvas_w, int canvas_h, int off_x, int off_y, int row0,
+              int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band, int force_exact,
+              void *stream) {
+  if (!src || !hinv || !col_cell || !row_cell || !out_band) return fail(APAP_E_BADARG, "null pointer");
+  if (src_h <= 0 || src_w <= 0 || canvas_w <= 0 || canvas_h <= 0 || grid_cols <= 0)
+    return fail(APAP_E_BADARG, "warp: sizes must be > 0");
+  if (centre && (centre_h <= 0 || centre_w <= 0)) return fail(APAP_E_BADARG, "warp: bad centre image size");
+  return launch_warp(src, src_h, src_w, hinv, col_cell, row_cell, grid_cols, canvas_w, canvas_h, off_x, off_y, row0,
+                     row1, centre, centre_h, centre_w, out_band, force_exact, static_cast<cudaStream_t>(stream));
+}
+
+int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream) {
+  if (!a || !b || !out) return fail(APAP_E_BADARG, "null pointer");
+  return launch_blend(a, b, out, n_px, static_cast<cudaStream_t>(stream));
+}
+
+int apap_fp32_probe(int iters, float *sink, double *flops, void *stream) {
+  if (!sink || iters <= 0) return fail(APAP_E_BADARG, "probe: bad arguments");
+  return launch_probe(iters, sink, flops, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

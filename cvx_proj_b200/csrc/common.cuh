@@ -1,0 +1,104 @@
+// Shared declarations of libapap_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "apap_b200.h"
+
+namespace apap {
+
+constexpr int kTerms = APAP_GRAM_TERMS;     // 24 distinct Gram sums
+constexpr int kRowFloats = APAP_KP_ROW;     // 28 floats = 112 B = 7 x 16 B per keypoint row
+constexpr int kChunk = APAP_KP_CHUNK;       // keypoint rows per smem stage
+constexpr int kHinvRow = APAP_HINV_ROW;     // 12 floats = 48 B per cell
+
+// Longest FP32 accumulation chain the Gram kernel runs before its sum leaves the register
+// (SURVEY.md finding 8: <= 1024 sequential FP32 terms, then a float64 combine, keeps the
+// per-cell H inside the 1e-4 gate; a single chain over all N does not).
+constexpr int kMaxChainChunks = 8;          // 8 x 128 = 1024 keypoints per split
+
+struct GramPlan {
+  int k_splits;
+  int chunks_per_split;
+  int cells_per_thread;     // register tile: cells handled by one thread (1, 2 or 4)
+  int cells_padded;         // multiple of 128 * cells_per_thread
+  int cell_tiles;
+};
+
+GramPlan make_gram_plan(int cells, int n_kp_padded, int sm_count);
+int sm_count_cached();
+
+// error plumbing (abi.cu)
+int fail(int code, const char *msg);
+int check_cuda(cudaError_t e, const char *what);
+
+// launchers (one per translation unit)
+int launch_gram(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
+                float k2, float gamma_sq, float *partials, cudaStream_t st);
+int launch_eig(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded,
+               float *out_h, int *out_sweeps, cudaStream_t st);
+int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
+                  double gamma, double *out, cudaStream_t st);
+int launch_warp(const uint8_t *src, int src_h, int src_w, const float *hinv, const uint16_t *col_cell,
+                const uint16_t *row_cell, int grid_cols, int canvas_w, int canvas_h, int off_x, int off_y,
+                int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
+                int force_exact, cudaStream_t st);
+int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, cudaStream_t st);
+int launch_probe(int iters, float *sink, double *flops, cudaStream_t st);
+
+// ---- small PTX helpers -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float add_rd(float a, float b) { return __fadd_rd(a, b); }
+
+}  // namespace apap

@@ -1,0 +1,58 @@
+// local_weight (second output of APAP.local_homography, reference pyviz/apap.py:150-153) and the
+// FP32 FMA-pipe probe that measures the denominator of the Gram kernel's roofline fraction.
+#include "common.cuh"
+
+namespace apap {
+
+// out[c][i] = max(exp(-sqrt(dx^2 + dy^2) * inv_sigma_sq), gamma) in float64, dx = anchor - keypoint
+// promoted exactly as numpy promotes float64 - float32.  Pure streaming writes (8 B / element).
+__global__ void __launch_bounds__(256) k_weight(const double *__restrict__ anchors, const float *__restrict__ kp_xy,
+                                                 int n_kp, double inv_sigma_sq, double gamma,
+                                                 double *__restrict__ out) {
+  const int cell = blockIdx.y;
+  const double vx = anchors[2 * cell], vy = anchors[2 * cell + 1];
+  double *dst = out + (size_t)cell * n_kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_kp; i += gridDim.x * blockDim.x) {
+    const float2 k = reinterpret_cast<const float2 *>(kp_xy)[i];
+    const double dx = vx - (double)k.x, dy = vy - (double)k.y;
+    const double w = exp(-(sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) * inv_sigma_sq));
+    dst[i] = w < gamma ? gamma : w;
+  }
+}
+
+int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq, double gamma,
+                  double *out, cudaStream_t st) {
+  if (cells == 0 || n_kp == 0) return 0;
+  if (cells > 65535) return fail(APAP_E_TOOBIG, "local_weight: at most 65535 cells per call (slice the grid)");
+  int bx = (n_kp + 255) / 256;
+  if (bx > 64) bx = 64;
+  k_weight<<<dim3(bx, cells), 256, 0, st>>>(anchors, kp_xy, n_kp, inv_sigma_sq, gamma, out);
+  return check_cuda(cudaGetLastError(), "k_weight launch");
+}
+
+// 16 independent FFMA chains per thread, 8 warps per CTA, 8 CTAs per SM: enough ILP and TLP to
+// saturate the FMA pipe.  flops = 2 * 16 * iters * threads.
+constexpr int kProbeThreads = 256;
+__global__ void __launch_bounds__(kProbeThreads) k_probe(int iters, float seed, float *sink) {
+  float a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = seed + (float)(threadIdx.x + k);
+  const float m = 0.999f + seed, c = 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 123456.789f) *sink = s;   // never true; keeps the chains alive
+}
+
+int launch_probe(int iters, float *sink, double *flops, cudaStream_t st) {
+  const int blocks = sm_count_cached() * 8;
+  k_probe<<<blocks, kProbeThreads, 0, st>>>(iters, 0.f, sink);
+  if (flops) *flops = 2.0 * 16.0 * (double)iters * (double)blocks * kProbeThreads;
+  return check_cuda(cudaGetLastError(), "k_probe launch");
+}
+
+}  // namespace apap

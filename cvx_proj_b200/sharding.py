@@ -1,0 +1,128 @@
+"""Multi-GPU partition of one APAP pass: cell rows and the canvas row bands they own.
+
+Cells are independent (pyviz/apap.py:147-168 carries nothing between iterations) and the
+pixel -> cell lookup is by canvas row (pyviz/apap.py:207), so rank g that owns the cell rows
+``[m0, m1)`` can compute those cells' homographies AND warp exactly the canvas rows whose
+``row_cell`` lies in ``[m0, m1)`` with no exchange in between (keypoints and the source image
+are replicated).  The only collective is the all-gather that assembles the panorama from the
+row bands (NCCL over NVLink on GPUs; the same code runs over gloo on CPU tensors in tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Shard:
+    rank: int
+    cell_row0: int      # first owned cell row
+    cell_row1: int      # one past the last owned cell row
+    px_row0: int        # first canvas row of the band
+    px_row1: int        # one past the last canvas row of the band
+
+    @property
+    def n_cell_rows(self) -> int:
+        return self.cell_row1 - self.cell_row0
+
+    @property
+    def n_px_rows(self) -> int:
+        return self.px_row1 - self.px_row0
+
+
+def split_rows(n_rows: int, world: int):
+    """Contiguous, balanced ``[(r0, r1)] * world`` (the first ``n_rows % world`` ranks get one more)."""
+    base, extra = divmod(n_rows, world)
+    out, r = [], 0
+    for g in range(world):
+        n = base + (1 if g < extra else 0)
+        out.append((r, r + n))
+        r += n
+    return out
+
+
+def plan_shards(row_cell: np.ndarray, grid_rows: int, world: int):
+    """One ``Shard`` per rank from the canvas-row -> cell-row table of the warp.
+
+    ``row_cell`` must be non-decreasing (true for any edge array from ``get_mesh``); the bands
+    then tile the canvas rows exactly once.
+    """
+    row_cell = np.asarray(row_cell, dtype=np.int64)
+    if row_cell.size and np.any(np.diff(row_cell) < 0):
+        raise ValueError("row_cell must be non-decreasing to shard the canvas by cell row")
+    shards = []
+    for g, (m0, m1) in enumerate(split_rows(grid_rows, world)):
+        r0 = int(np.searchsorted(row_cell, m0, side="left"))
+        r1 = int(np.searchsorted(row_cell, m1, side="left"))
+        shards.append(Shard(g, m0, m1, r0, r1))
+    return shards
+
+
+def gather_bands(band, shards, canvas_w: int, group=None):
+    """All-gather the row bands into the full ``[canvas_h, canvas_w, 3]`` uint8 panorama.
+
+    ``band`` is this rank's ``[n_px_rows, canvas_w, 3]`` uint8 tensor (CUDA -> NCCL, CPU -> gloo).
+    Bands differ by at most a few rows, so each is padded to the tallest band for one
+    ``all_gather_into_tensor`` and the padding is dropped when the rows are stitched.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    assert world == len(shards)
+    tallest = max(s.n_px_rows for s in shards)
+    row_bytes = canvas_w * 3
+    mine = torch.zeros((tallest, row_bytes), dtype=torch.uint8, device=band.device)
+    mine[: band.shape[0]] = band.reshape(band.shape[0], row_bytes)
+    everyone = torch.empty((world, tallest, row_bytes), dtype=torch.uint8, device=band.device)
+    dist.all_gather_into_tensor(everyone.view(-1), mine.view(-1), group=group)
+    parts = [everyone[s.rank, : s.n_px_rows] for s in shards]
+    return torch.cat(parts, dim=0).reshape(-1, canvas_w, 3)
+
+
+class ShardedAPAP:
+    """One APAP pass split over the ranks of a ``torch.distributed`` group.
+
+    Every rank holds the full keypoint set and source image; it solves its cell rows (K1 + K2),
+    inverts them on the host like the reference, and warps its row band (K3).  ``panorama()``
+    is the one collective.
+    """
+
+    def __init__(self, stitcher, mesh, grid_rows: int, grid_cols: int, rank: int, world: int):
+        from .apap import cell_lookup_tables
+
+        self.stitcher = stitcher
+        self.mesh = np.asarray(mesh)
+        self.grid_rows, self.grid_cols = grid_rows, grid_cols
+        self.col_cell, self.row_cell = cell_lookup_tables(self.mesh, int(stitcher.final_width),
+                                                          int(stitcher.final_height), grid_rows, grid_cols)
+        self.shards = plan_shards(self.row_cell, grid_rows, world)
+        self.me = self.shards[rank]
+
+    def local_homography(self, src_point, dst_point, vertices):
+        """H for the owned cell rows only: ``[n_cell_rows, grid_cols, 3, 3]`` float32."""
+        s = self.me
+        h, _ = self.stitcher.local_homography(src_point, dst_point, np.asarray(vertices)[s.cell_row0:s.cell_row1])
+        return h
+
+    def local_warp_band(self, ori_img, local_h_rows):
+        """Warp the owned canvas rows.  ``local_h_rows`` = this rank's rows of H (inverted in place,
+        like ``APAP.local_warp``).  Returns a device tensor ``[n_px_rows, canvas_w, 3]``."""
+        from . import _runtime as rt
+        from .apap import build_hinv_rows
+
+        st, s = self.stitcher, self.me
+        torch, device = rt.torch_cuda(st.device)
+        local_h_rows[...] = np.linalg.inv(local_h_rows)
+        full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
+        full[...] = np.eye(3, dtype=np.float32)
+        full[s.cell_row0:s.cell_row1] = local_h_rows
+        rows = build_hinv_rows(full, self.col_cell, self.row_cell, int(st.offset_x), int(st.offset_y),
+                               int(ori_img.shape[1]), int(ori_img.shape[0]))
+        src_dev = ori_img if not isinstance(ori_img, np.ndarray) else rt.to_device(torch, device, ori_img)
+        return st.warp_device(src_dev, rt.to_device(torch, device, rows), rt.to_device(torch, device, self.col_cell),
+                              rt.to_device(torch, device, self.row_cell), self.grid_cols, s.px_row0, s.px_row1)
+
+    def panorama(self, band, group=None):
+        return gather_bands(band, self.shards, int(self.stitcher.final_width), group)

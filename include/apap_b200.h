@@ -1,0 +1,133 @@
+/*
+ * apap_b200.h -- C ABI of libapap_b200.so: the APAP (moving-DLT + mesh warp) hot path of
+ * Enigmatisms/cvx_proj as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI today: the path is plain Python (pyviz/apap.py, pyviz/apap_utils.py).
+ * Each entry point below names the reference code it replaces.  The Python host layer
+ * (cvx_proj_b200/apap.py, apap_utils.py) binds these with ctypes and keeps the reference's
+ * own call surface; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller (no hidden allocation, no
+ *     hidden host<->device copy); `stream` is a cudaStream_t passed as void*; calls are
+ *     asynchronous on that stream;
+ *   - return value 0 = ok; > 0 = a cudaError_t; < 0 = an APAP_E_* argument error;
+ *     apap_last_error() gives a thread-local message for the last non-zero return;
+ *   - a "cell" is one mesh cell of the APAP grid (row-major, row = y cell, col = x cell), a
+ *     "keypoint" one matched pair, a "canvas" the stitched output image (HxWx3 uint8,
+ *     OpenCV BGR order, rows packed, 3 bytes per pixel).
+ */
+#ifndef APAP_B200_H
+#define APAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APAP_ABI_VERSION 1
+
+/* Layout constants shared with the host layer. */
+#define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
+#define APAP_KP_ROW     28   /* floats per keypoint row: 24 product terms, kx, ky, 2 pad (112 B)  */
+#define APAP_KP_CHUNK   128  /* keypoint rows per shared-memory stage; tables are padded to this  */
+#define APAP_HINV_ROW   12   /* floats per cell of the inverse grid: 9 H^-1, eps_x, eps_y, pad    */
+
+#define APAP_E_BADARG   (-1)
+#define APAP_E_ALIGN    (-2)
+#define APAP_E_TOOBIG   (-3)
+
+int apap_abi_version(void);
+const char *apap_last_error(void);
+
+/* Number of SMs of the current device (grid sizing, reporting). */
+int apap_device_sm_count(int *sm_count);
+
+/*
+ * Plan the moving-DLT contraction: how many keypoint splits the Gram kernel uses for
+ * (cells, n_kp_padded) and how many bytes of partial sums it needs per scene.
+ *   partial layout: float [k_splits][APAP_GRAM_TERMS][cells_padded]   (term-major, coalesced)
+ */
+int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
+                   size_t *partial_bytes_per_scene);
+
+/*
+ * K1 -- weights + Gram contraction.  Replaces, for every cell, pyviz/apap.py:150-152 (the
+ * weight w_i = max(exp(-|v - x_i| / sigma^2), gamma)) and the row scaling + SVD input build of
+ * pyviz/apap.py:159: it accumulates S_t(cell) = sum_i w_i^2 * kp_table[i][t] for the 24 terms.
+ *   kp_table : float [batch][n_kp_padded][APAP_KP_ROW]; rows past the real keypoints are zero
+ *   anchors  : float [batch][cells][2]  (x, y) cell anchor points (get_vertice), float32
+ *   partials : float [batch][k_splits][24][cells_padded]
+ *   neg2_log2e_inv_sigma_sq = -2*log2(e)/sigma^2 ; gamma_sq = gamma^2
+ */
+int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells,
+                       int n_kp_padded, float neg2_log2e_inv_sigma_sq, float gamma_sq,
+                       float *partials, void *stream);
+
+/*
+ * K2 -- per-cell 9x9 symmetric eigensolve + de-normalisation.  Replaces cv.SVDecomp + V[-1]
+ * (pyviz/apap.py:160-161) and pyviz/apap.py:164-168: sums the k_splits partials in float64,
+ * expands the 24 sums to the 9x9 Gram matrix, runs cyclic Jacobi, takes the eigenvector of the
+ * smallest eigenvalue h, and stores float32 H = T2inv * reshape(h,3,3) * T1, divided by H[2][2].
+ *   tmats : double [batch][18] = T2inv (row-major 3x3) then T1, T2inv = inv(N2) inv(C2), T1 = C1 N1
+ *   out_h : float [batch][cells][9]
+ *   out_sweeps : optional int32 [batch][cells] Jacobi sweeps used (NULL to skip)
+ */
+int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells,
+                    int n_kp_padded, float *out_h, int *out_sweeps, void *stream);
+
+/* K1 + K2 back to back on `stream` (what APAP.local_homography calls). */
+int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats,
+                          int batch, int cells, int n_kp_padded,
+                          float neg2_log2e_inv_sigma_sq, float gamma_sq,
+                          float *partials, float *out_h, int *out_sweeps, void *stream);
+
+/*
+ * Second output of APAP.local_homography (pyviz/apap.py:144,153): float64 weights
+ *   out[c][i] = max(exp(-|anchor_c - kp_i| / sigma^2), gamma),  c in [0, cells), i in [0, n_kp)
+ *   anchors : double [cells][2];  kp_xy : float [n_kp][2]
+ */
+int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp,
+                      double inv_sigma_sq, double gamma, double *out, void *stream);
+
+/*
+ * K3 -- mesh warp.  Replaces the pixel loop of APAP.local_warp (pyviz/apap.py:206-215): for the
+ * canvas rows [row0, row1) looks the cell up (col_cell / row_cell tables = np.where(k < edges)
+ * of :207,:209), applies that cell's H^-1 to (j - off_x, i - off_y, 1), divides, and copies
+ * src[int(ty)][int(tx)] when 0 < tx < src_w and 0 < ty < src_h (else leaves 0).  Pixel selection
+ * is bit-identical to the reference's float64 arithmetic: a float32 fast path decides every pixel
+ * whose coordinates are farther than the cell's guard band (eps_x, eps_y of the hinv row) from an
+ * integer, the rest are recomputed in float64.
+ *   hinv      : float [grid_rows*grid_cols][APAP_HINV_ROW]
+ *   col_cell  : uint16 [canvas_w], row_cell : uint16 [canvas_h]
+ *   out_band  : uint8 [(row1-row0)][canvas_w][3], 4-byte aligned; receives rows row0..row1-1
+ *   centre    : optional uint8 [centre_h][centre_w][3] pasted at (off_x, off_y) and blended with
+ *               the warped pixel by the uniform_blend rule (fused K3+K4, pyviz/apap.py:259-261);
+ *               NULL = plain warp
+ *   force_exact : non-zero = every pixel takes the float64 path (validation switch)
+ */
+int apap_warp(const uint8_t *src, int src_h, int src_w, const float *hinv,
+              const uint16_t *col_cell, const uint16_t *row_cell, int grid_cols,
+              int canvas_w, int canvas_h, int off_x, int off_y, int row0, int row1,
+              const uint8_t *centre, int centre_h, int centre_w,
+              uint8_t *out_band, int force_exact, void *stream);
+
+/*
+ * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,
+ * per pixel of n_px 3-byte pixels.  All three pointers 16-byte aligned.
+ */
+int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream);
+
+/*
+ * FP32 FMA-pipe probe: runs `iters` x 16 dependent-chain-free FFMAs per thread on every SM and
+ * returns the flop count; the caller times it with events to get the measured FP32 peak that the
+ * Gram kernel's roofline fraction is quoted against.  sink: float [1] device scratch.
+ */
+int apap_fp32_probe(int iters, float *sink, double *flops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APAP_B200_H */

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python surface)
+against the golden vectors of the live reference and against the oracle.
+
+Tolerances (SURVEY.md section 8c / BASELINE.json north_star):
+  per-cell H: max|S2 (H - Href) S1^-1| / max|S2 Href S1^-1| <= 1e-4, S = diag(1/L, 1/L, 1)
+  warp, blend, lookup tables, in-place inverse: bit-exact
+  local_weight (float64): relative 1e-13
+"""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+from cvx_proj_b200 import apap_utils, sharding, synth
+from cvx_proj_b200 import _runtime as rt
+from cvx_proj_b200.apap import APAP, cell_lookup_tables
+from oracle import apap_oracle as orc
+
+pytestmark = pytest.mark.gpu
+H_GATE = 1e-4
+
+
+def _stitcher(sc, **kw):
+    return APAP(kw.get("gamma", sc.gamma), kw.get("sigma", sc.sigma), [sc.final_w, sc.final_h],
+                [sc.offset_x, sc.offset_y])
+
+
+def _herr(h, ref, sc):
+    return orc.h_error_normalised(h, ref, max(sc.final_w, sc.final_h))
+
+
+# ------------------------------------------------------------------------------- moving DLT
+@pytest.mark.parametrize("name", ["tiny", "mini"])
+def test_local_homography_vs_reference_golden(golden, name):
+    g = golden(f"ref_{name}.npz")
+    sc = synth.make_scene(name)
+    h, w = _stitcher(sc).local_homography(g["src"], g["dst"], g["vertices"])
+    assert h.shape == g["H"].shape and h.dtype == np.float32
+    assert _herr(h, g["H"], sc).max() <= H_GATE
+    assert w.shape == g["W"].shape
+    np.testing.assert_allclose(np.asarray(w), g["W"], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(w[2, 3], g["W"][2, 3], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(w[1], g["W"][1], rtol=1e-13, atol=0)
+
+
+def test_local_homography_c1_full_vs_reference(golden):
+    g = golden("ref_c1.npz")
+    sc = synth.make_scene("c1")
+    h, w = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+    err = _herr(h, g["H"], sc)
+    print(f"c1: normalised H error max {err.max():.3e}, raw elementwise {orc.h_error_raw(h, g['H']):.3e}")
+    assert err.max() <= H_GATE
+    np.testing.assert_allclose(np.asarray(w)[::9, ::9, ::7], g["W_sample"], rtol=1e-13, atol=0)
+
+
+def test_clamped_weights(golden):
+    g = golden("ref_tiny_sigma8.npz")
+    sc = synth.make_scene("tiny")
+    h, w = _stitcher(sc, sigma=8.0).local_homography(sc.src, sc.dst, sc.vertices)
+    assert _herr(h, g["H"], sc).max() <= H_GATE
+    wa = np.asarray(w)
+    np.testing.assert_allclose(wa, g["W"], rtol=1e-13, atol=0)
+    assert np.array_equal(wa == 0.5, g["W"] == 0.5)
+
+
+def test_c2_spot_cells_vs_reference_and_full_grid_vs_oracle(golden):
+    s = golden("ref_c2_spot.npz")
+    sc = synth.make_scene("c2")
+    h, _ = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+    got = h[s["rows"]][:, s["cols"]]
+    err = _herr(got, s["H"], sc)
+    print(f"c2 spot: normalised H error max {err.max():.3e}, raw {orc.h_error_raw(got, s['H']):.3e}")
+    assert err.max() <= H_GATE
+    # every 5th row and column of the full grid against the float64 Gram oracle
+    sub = sc.vertices[::5, ::5]
+    ref = orc.local_homography_gram64(sc.src, sc.dst, sub, sc.gamma, sc.sigma)
+    assert _herr(h[::5, ::5], ref, sc).max() <= H_GATE
+
+
+@pytest.mark.parametrize("n_kp", [4, 7, 128, 129, 1500, 9000])
+def test_ragged_keypoint_counts(n_kp):
+    sc = synth.make_scene("mini", n_kp=n_kp, mesh=6)
+    h, _ = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+    if n_kp >= 7:        # fewer than ~5 pairs leave the DLT rank-deficient; the reference's answer is arbitrary there
+        ref = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+        assert _herr(h, ref, sc).max() <= H_GATE
+    assert np.isfinite(h).all() or n_kp < 7
+
+
+def test_exact_homography_gives_global_h_everywhere():
+    sc = synth.make_scene("mini", n_kp=400)
+    hom = np.concatenate([sc.src.astype(np.float64), np.ones((400, 1))], 1) @ sc.h_gt.T
+    dst = (hom[:, :2] / hom[:, 2:3]).astype(np.float32)
+    h, _ = _stitcher(sc).local_homography(sc.src, dst, sc.vertices)
+    want = np.broadcast_to((sc.h_gt / sc.h_gt[2, 2]).astype(np.float32), h.shape)
+    # inputs are float32-rounded, so the fit is exact only to ~1e-5 of a pixel scale
+    assert _herr(h, want, sc).max() <= 2e-4
+
+
+def test_all_weights_clamped_equals_unweighted_dlt():
+    sc = synth.make_scene("mini")
+    h, _ = _stitcher(sc, gamma=1.0).local_homography(sc.src, sc.dst, sc.vertices)   # max(w, 1) == 1
+    ref = orc.local_homography_svd(sc.src, sc.dst, sc.vertices[:1, :1], 1.0, sc.sigma)[0, 0]
+    assert _herr(h, np.broadcast_to(ref, h.shape), sc).max() <= H_GATE
+    assert np.abs(h - h[0, 0]).max() <= 1e-6 * np.abs(h[0, 0]).max()
+
+
+def test_keypoint_permutation_invariance():
+    sc = synth.make_scene("mini", n_kp=700)
+    st = _stitcher(sc)
+    h0, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    perm = np.random.default_rng(11).permutation(700)
+    h1, _ = st.local_homography(sc.src[perm], sc.dst[perm], sc.vertices)
+    assert _herr(h1, h0, sc).max() <= H_GATE
+
+
+def test_batch_equals_single_pairs_bitwise():
+    scenes = [synth.make_scene("mini", seed=s, n_kp=n) for s, n in ((0, 200), (1, 333), (2, 120))]
+    st = _stitcher(scenes[0])
+    many = st.local_homography_batch([s.src for s in scenes], [s.dst for s in scenes], scenes[0].vertices)
+    for sc, hb in zip(scenes, many):
+        h1, _ = st.local_homography(sc.src, sc.dst, scenes[0].vertices)
+        assert np.array_equal(hb, h1)
+
+
+def test_cell_row_sharding_is_bitwise_identical():
+    """Rows solved on their own (what a rank of the multi-GPU run does) equal the same rows of the
+    full-grid solve bit for bit: the FP32 chain boundaries depend only on the keypoint count."""
+    sc = synth.make_scene("c1", mesh=40)
+    st = _stitcher(sc)
+    full, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    for r0, r1 in sharding.split_rows(40, 3):
+        part, _ = st.local_homography(sc.src, sc.dst, sc.vertices[r0:r1])
+        assert np.array_equal(part, full[r0:r1])
+
+
+# --------------------------------------------------------------------------------- mesh warp
+@pytest.mark.parametrize("name", ["tiny", "mini"])
+def test_local_warp_bit_exact_vs_reference_golden(golden, name):
+    g = golden(f"ref_{name}.npz")
+    sc = synth.make_scene(name)
+    img = sc.image(1)
+    h = g["H"].copy()
+    warped = _stitcher(sc).local_warp(img, h, g["mesh"], progress=True)
+    assert warped.dtype == np.uint8 and np.array_equal(warped, g["warped"])
+    assert np.array_equal(h, g["H_inverted_in_place"])          # the in-place inversion side effect
+    centre = synth.make_image(sc.width, sc.height, seed=2)
+    pasted = orc.paste_centre(warped, centre, (sc.offset_x, sc.offset_y))
+    assert np.array_equal(apap_utils.uniform_blend(warped, pasted), g["blended"])
+    fused = _stitcher(sc).local_warp_blend(img, g["H"].copy(), g["mesh"], centre)
+    assert np.array_equal(fused, g["blended"])
+
+
+def test_local_warp_c1_rows_vs_reference(golden):
+    g = golden("ref_c1.npz")
+    sc = synth.make_scene("c1")
+    img = sc.image(1)
+    warped = _stitcher(sc).local_warp(img, g["H"].copy(), sc.mesh)
+    crc = np.array([zlib.crc32(np.ascontiguousarray(r).tobytes()) for r in warped], dtype=np.uint32)
+    bad = np.flatnonzero(crc != g["warped_row_crc"])
+    assert bad.size == 0, f"rows differ: {bad[:10]}"
+    assert hashlib.sha256(warped.tobytes()).hexdigest() == str(g["warped_sha"])
+
+
+def test_fast_path_equals_forced_float64_path():
+    sc = synth.make_scene("c1")
+    img = sc.image(1)
+    st = _stitcher(sc)
+    h = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+    a = st._warp(img, h.copy(), sc.mesh)
+    b = st._warp(img, h.copy(), sc.mesh, force_exact=True)
+    assert np.array_equal(a, b)
+    assert (a.max(axis=-1) > 0).mean() > 0.3
+
+
+def test_local_warp_c2_full_size_vs_oracle():
+    sc = synth.make_scene("c2")
+    img = sc.image(1)
+    st = _stitcher(sc)
+    h, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    want = orc.local_warp(img, orc.invert_grid(h), sc.mesh, (sc.final_w, sc.final_h), (sc.offset_x, sc.offset_y))
+    got = st.local_warp(img, h, sc.mesh)
+    diff = np.flatnonzero((got != want).any(axis=-1).ravel())
+    assert diff.size == 0, f"{diff.size} pixels differ, first {diff[:5]}"
+
+
+def test_identity_and_translation_hit_exact_integers():
+    """Integer-valued coordinates sit exactly on the truncation boundary: every pixel is decided
+    by the float64 path and must match the reference rule (strict bounds drop row/column 0)."""
+    rng = np.random.default_rng(4)
+    img = rng.integers(1, 256, size=(90, 120, 3), dtype=np.uint8)
+    st = APAP(0.5, 100, [150, 100], [7, 5])
+    mesh = apap_utils.get_mesh((150, 100), 5)
+    h = np.tile(np.eye(3, dtype=np.float32), (4, 4, 1, 1))
+    h[..., 0, 2] = 3.0
+    got = st.local_warp(img, h.copy(), mesh)
+    want = orc.local_warp(img, orc.invert_grid(h), mesh, (150, 100), (7, 5))
+    assert np.array_equal(got, want)
+    assert got.any() and not got[:, :7 + 3 + 1].any()
+
+
+def test_warp_degenerate_cells():
+    """Singular-ish / sign-changing denominators inside a cell (whole cell takes the exact path)."""
+    rng = np.random.default_rng(9)
+    img = rng.integers(1, 256, size=(64, 64, 3), dtype=np.uint8)
+    st = APAP(0.5, 100, [96, 80], [0, 0])
+    mesh = apap_utils.get_mesh((96, 80), 4)
+    inv = np.tile(np.eye(3, dtype=np.float32), (3, 3, 1, 1))
+    inv[0, 0, 2] = [0.05, 0.0, -0.5]         # t2 crosses zero at x = 10
+    inv[1, 1, 2] = [0.0, 0.0, 1e-30]         # enormous coordinates
+    inv[2, 2] = [[1.3, 0.2, -4.1], [0.1, 0.9, 2.2], [1e-3, -2e-3, 1.0]]
+    h = np.linalg.inv(inv.astype(np.float64)).astype(np.float32)
+    got = st.local_warp(img, h.copy(), mesh)
+    want = orc.local_warp(img, orc.invert_grid(h), mesh, (96, 80), (0, 0))
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("fw,fh", [(1, 1), (3, 2), (5, 7), (130, 3)])
+def test_warp_tiny_and_ragged_canvases(fw, fh):
+    rng = np.random.default_rng(fw * 10 + fh)
+    img = rng.integers(1, 256, size=(9, 11, 3), dtype=np.uint8)
+    st = APAP(0.5, 100, [fw, fh], [1, 1])
+    mesh = apap_utils.get_mesh((fw, fh), 3)
+    h = np.tile(np.array([[0.9, 0.05, 0.3], [0.02, 1.1, -0.2], [1e-3, 0, 1]], np.float32), (2, 2, 1, 1))
+    got = st.local_warp(img, h.copy(), mesh)
+    want = orc.local_warp(img, orc.invert_grid(h), mesh, (fw, fh), (1, 1))
+    assert got.shape == (fh, fw, 3) and np.array_equal(got, want)
+
+
+def test_row_bands_tile_the_full_warp():
+    import torch
+    sc = synth.make_scene("c1", mesh=30)
+    img = sc.image(1)
+    st = _stitcher(sc)
+    h = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+    full = st.local_warp(img, h.copy(), sc.mesh)
+    col, row = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, 30, 30)
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            sh = sharding.ShardedAPAP(st, sc.mesh, 30, 30, rank, world)
+            band = sh.local_warp_band(img, h[sh.me.cell_row0:sh.me.cell_row1].copy())
+            assert band.shape[0] == sh.me.n_px_rows
+            parts.append(band.cpu().numpy())
+        assert np.array_equal(np.concatenate(parts, 0), full)
+    torch.cuda.synchronize()
+
+
+def test_device_tensor_input_stays_on_device():
+    import torch
+    sc = synth.make_scene("mini")
+    img = sc.image(1)
+    st = _stitcher(sc)
+    h = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+    host = st.local_warp(img, h.copy(), sc.mesh)
+    dev = st.local_warp(torch.from_numpy(img).cuda(), h.copy(), sc.mesh)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+
+
+# --------------------------------------------------------------------------------------- blend
+def test_uniform_blend_golden_and_tails(golden):
+    g = golden("ref_blend.npz")
+    assert np.array_equal(apap_utils.uniform_blend(g["a"], g["b"]), g["out"])
+    rng = np.random.default_rng(2)
+    for hh, ww in ((1, 1), (1, 15), (1, 16), (1, 17), (5, 13), (64, 100)):
+        a = rng.integers(0, 256, size=(hh, ww, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, size=(hh, ww, 3), dtype=np.uint8)
+        a[rng.random((hh, ww)) < 0.3] = 0
+        b[rng.random((hh, ww)) < 0.3] = 0
+        assert np.array_equal(apap_utils.uniform_blend(a, b), orc.uniform_blend(a, b)), (hh, ww)
+
+
+def test_uniform_blend_full_size_properties():
+    sc = synth.make_scene("c2")
+    a = synth.make_image(sc.final_w, sc.final_h, seed=3)
+    b = synth.make_image(sc.final_w, sc.final_h, seed=4)
+    a[: sc.final_h // 3] = 0
+    b[2 * sc.final_h // 3:] = 0
+    out = apap_utils.uniform_blend(a, b)
+    assert np.array_equal(out, orc.uniform_blend(a, b))
+    assert np.array_equal(apap_utils.uniform_blend(b, a), out)                      # symmetric
+    assert np.array_equal(apap_utils.uniform_blend(a, np.zeros_like(a)), a)        # black is neutral
+    assert np.array_equal(apap_utils.uniform_blend(a, a), np.where(a.max(-1, keepdims=True) > 0, a, 0))
+
+
+def test_errors_surface_as_exceptions():
+    st = APAP(0.5, 100, [64, 48], [0, 0])
+    with pytest.raises(ValueError):
+        st.local_homography(np.zeros((10, 3), np.float32), np.zeros((10, 2), np.float32), np.zeros((2, 2, 2)))
+    with pytest.raises(ValueError):
+        apap_utils.uniform_blend(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 5, 3), np.uint8))
+    lib = rt.load_library()
+    assert lib.apap_blend(None, None, None, 10, None) != 0
+    assert b"null" in lib.apap_last_error()

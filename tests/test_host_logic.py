@@ -1,0 +1,251 @@
+"""CPU tests of the host layer: the numpy pieces kept bit-identical to the reference, the
+kernel-input builders, the guard-band logic of the warp's float32 fast path (emulated in numpy),
+the C-ABI library (loads, exports every declared symbol) and the no-fallback rule."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cvx_proj_b200 import _runtime as rt
+from cvx_proj_b200 import apap as papap
+from cvx_proj_b200 import apap_utils, sharding, synth
+from cvx_proj_b200.apap import APAP
+from oracle import apap_oracle as orc
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["tiny", "mini"])
+def test_static_methods_bit_exact_vs_reference(golden, name):
+    g = golden(f"ref_{name}.npz")
+    n1, nf1 = APAP.getNormalize2DPts(g["src"])
+    n2, nf2 = APAP.getNormalize2DPts(g["dst"])
+    c1, c2 = APAP.getConditionerFromPts(nf1), APAP.getConditionerFromPts(nf2)
+    cf1, cf2 = APAP.point_normalize(nf1, c1), APAP.point_normalize(nf2, c2)
+    dlt = APAP.matrix_generate(g["src"].shape[0], cf1, cf2)
+    for got, key in ((n1, "N1"), (n2, "N2"), (nf1, "nf1"), (nf2, "nf2"), (c1, "C1"), (c2, "C2"),
+                     (cf1, "cf1"), (cf2, "cf2"), (dlt, "A")):
+        assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+
+
+@pytest.mark.parametrize("name", ["tiny", "mini"])
+def test_utils_bit_exact_vs_reference(golden, name):
+    g = golden(f"ref_{name}.npz")
+    sc = synth.make_scene(name)
+    img = np.zeros((sc.height, sc.width, 3), np.uint8)
+    assert [int(v) for v in apap_utils.final_size(img, img, g["h_gt"])] == list(g["final_size"])
+    fw, fh, ox, oy = (int(v) for v in g["final_size"])
+    assert np.array_equal(apap_utils.get_mesh((fw, fh), sc.mesh_cells + 1), g["mesh"])
+    assert np.array_equal(apap_utils.get_vertice((fw, fh), sc.mesh_cells, (ox, oy)), g["vertices"])
+
+
+def test_warp_coordinate_estimate():
+    h = np.array([[1.5, 0, 2], [0, 2, -1], [0, 0, 2]], dtype=np.float32)
+    out = APAP.warp_coordinate_estimate(np.array([4, 6, 1]), h)
+    assert out.dtype == np.float64 and np.array_equal(out, [4.0, 5.5, 1.0])
+
+
+def test_kp_table_reproduces_weighted_gram(golden):
+    g = golden("ref_mini.npz")
+    src, dlt = g["src"], g["A"]
+    tab = papap.build_kp_table(src, dlt)
+    n = src.shape[0]
+    assert tab.shape == (256, rt.KP_ROW) and tab.dtype == np.float32
+    assert not tab[n:].any() and np.array_equal(tab[:n, 24:26], src)
+    w = g["W"][3, 5]
+    a64 = dlt.astype(np.float64) * np.repeat(w, 2)[:, None]
+    want = a64.T @ a64
+    got = papap.expand_gram((w[:, None] ** 2 * tab[:n, :24].astype(np.float64)).sum(0))
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    assert np.array_equal(got, got.T)
+
+
+def test_cell_lookup_matches_reference_rule(golden):
+    g = golden("ref_mini.npz")
+    fw, fh = int(g["final_size"][0]), int(g["final_size"][1])
+    mesh = g["mesh"]
+    col, row = papap.cell_lookup_tables(mesh, fw, fh, 16, 16)
+    assert col.dtype == np.uint16 and row.dtype == np.uint16
+    for j in range(fw):
+        assert col[j] == np.where(j < mesh[0])[0][0] - 1
+    for i in range(fh):
+        assert row[i] == np.where(i < mesh[1])[0][0] - 1
+    assert np.array_equal(col, orc.cell_lookup(mesh[0], fw)) and np.array_equal(row, orc.cell_lookup(mesh[1], fh))
+    with pytest.raises(IndexError):            # canvas wider than the mesh: the reference's [0][0] fails
+        papap.cell_lookup_tables(mesh, fw + 5, fh, 16, 16)
+    with pytest.raises(IndexError):            # mesh finer than the homography grid
+        papap.cell_lookup_tables(mesh, fw, fh, 8, 8)
+
+
+def _emulate_fast_path(rows, col, row, fw, fh, ox, oy, sw, sh, rng):
+    """float32 fast path of k_warp (csrc/warp_blend.cu fast_lookup) in numpy; fma emulated through
+    float64 (products of two float32 are exact there), rcp perturbed by +-1 ulp."""
+    f32 = np.float32
+    cell = row[:, None].astype(np.int64) * (int(col.max()) + 1) + col[None, :]
+    r = rows[cell]                                                            # [fh, fw, 12]
+    x = (np.arange(fw) - ox).astype(f32)[None, :]
+    y = (np.arange(fh) - oy).astype(f32)[:, None]
+    fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)  # noqa
+    t0 = fma(r[..., 0], x + 0 * y, fma(r[..., 1], y + 0 * x, r[..., 2]))
+    t1 = fma(r[..., 3], x + 0 * y, fma(r[..., 4], y + 0 * x, r[..., 5]))
+    t2 = fma(r[..., 6], x + 0 * y, fma(r[..., 7], y + 0 * x, r[..., 8]))
+    with np.errstate(all="ignore"):
+        rc = (f32(1) / t2).astype(f32)
+        rc = np.where(rng.random(rc.shape) < 0.5, np.nextafter(rc, f32(np.inf)), np.nextafter(rc, f32(-np.inf)))
+        out = []
+        for t in (t0, t1):
+            q = (t * rc).astype(f32)
+            q = fma(fma(-q, t2, t), rc, q)
+            q = np.where(np.isnan(q), f32(-0.5), q)
+            out.append(np.minimum(np.maximum(q, f32(-0.5)), f32(4194303.5)))
+    qx, qy = out
+    ix, iy = np.floor(qx), np.floor(qy)
+    fx, fy = qx - ix, qy - iy
+    flagged = (np.abs(fx - f32(0.5)) > f32(0.5) - r[..., 9]) | (np.abs(fy - f32(0.5)) > f32(0.5) - r[..., 10])
+    inb = (ix >= 0) & (ix < sw) & (iy >= 0) & (iy < sh)
+    off = np.where(inb, (iy.astype(np.int64) * sw + ix.astype(np.int64)), -1)
+    return off, flagged
+
+
+def _exact_path(inv_h, col, row, fw, fh, ox, oy, sw, sh):
+    h = inv_h[row[:, None], col[None, :]].astype(np.float64)
+    x = (np.arange(fw) - ox).astype(np.float64)[None, :]
+    y = (np.arange(fh) - oy).astype(np.float64)[:, None]
+    t0 = h[..., 0, 0] * x + h[..., 0, 1] * y + h[..., 0, 2]
+    t1 = h[..., 1, 0] * x + h[..., 1, 1] * y + h[..., 1, 2]
+    t2 = h[..., 2, 0] * x + h[..., 2, 1] * y + h[..., 2, 2]
+    with np.errstate(all="ignore"):
+        tx, ty = t0 / t2, t1 / t2
+    ok = (0 < tx) & (tx < sw) & (0 < ty) & (ty < sh)
+    return np.where(ok, np.where(ok, ty, 0).astype(np.int64) * sw + np.where(ok, tx, 0).astype(np.int64), -1)
+
+
+@pytest.mark.parametrize("name,scale", [("mini", 1.0), ("c1", 1.0), ("mini", 40.0)])
+def test_guard_band_makes_fast_path_exact(golden, name, scale):
+    """Every pixel the float32 fast path does NOT flag must pick the reference's source pixel."""
+    g = golden(f"ref_{name}.npz")
+    sc = synth.make_scene(name)
+    inv = g["H_inverted_in_place"].copy()
+    fw, fh, ox, oy = sc.final_w, sc.final_h, sc.offset_x, sc.offset_y
+    sw, sh = sc.width, sc.height
+    if scale != 1.0:   # stress: 8K-like magnitudes (coordinates and offsets scaled up)
+        s = np.diag([scale, scale, 1.0])
+        inv = (s @ inv.astype(np.float64) @ np.linalg.inv(s)).astype(np.float32)
+        fw, fh, ox, oy, sw, sh = (int(v * scale) for v in (fw, fh, ox, oy, sw, sh))
+        fh = min(fh, 600)
+    mesh = apap_utils.get_mesh((fw, fh), sc.mesh_cells + 1)
+    col, row = papap.cell_lookup_tables(mesh, fw, fh, sc.mesh_cells, sc.mesh_cells)
+    rows = papap.build_hinv_rows(inv, col, row, ox, oy, sw, sh)
+    off, flagged = _emulate_fast_path(rows, col, row, fw, fh, ox, oy, sw, sh, np.random.default_rng(3))
+    want = _exact_path(inv, col, row, fw, fh, ox, oy, sw, sh)
+    assert np.array_equal(off[~flagged], want[~flagged])
+    assert flagged.mean() < 0.05, flagged.mean()
+    assert (want >= 0).mean() > 0.3        # the case does exercise in-bounds pixels
+
+
+def test_guard_band_degenerate_cells_go_exact():
+    inv = np.tile(np.eye(3, dtype=np.float32), (2, 2, 1, 1))
+    inv[0, 0, 2] = [0.02, 0.0, -0.5]          # denominator crosses zero inside the cell
+    inv[1, 1] = np.nan
+    mesh = apap_utils.get_mesh((100, 80), 3)
+    col, row = papap.cell_lookup_tables(mesh, 100, 80, 2, 2)
+    rows = papap.build_hinv_rows(inv, col, row, 0, 0, 64, 64).reshape(2, 2, -1)
+    assert rows[0, 0, 9] >= 1.0 and rows[0, 0, 10] >= 1.0
+    assert rows[1, 1, 9] >= 1.0 and rows[1, 1, 10] >= 1.0
+    assert rows[0, 1, 9] < 1e-3 and rows[1, 0, 10] < 1e-3
+
+
+def test_gram_plan_depends_only_on_keypoints():
+    seen = {}
+    for cells in (64, 10_000, 40_000, 160_000):
+        for n_pad in (128, 512, 2048, 5120, 20096, 65536):
+            ks, cp, nb = rt.gram_plan(cells, n_pad)
+            assert seen.setdefault(n_pad, ks) == ks          # same split structure however the grid is sharded
+            assert cp >= cells and cp % 512 == 0 and nb == ks * 24 * cp * 4
+            assert -(-n_pad // ks) <= 1024 + 128             # FP32 chains stay <= 1024 keypoints (+ rounding to a chunk)
+    with pytest.raises(rt.ApapError):
+        rt.gram_plan(10, 100)                                # not a multiple of the chunk
+
+
+def test_library_exports_every_declared_symbol():
+    lib = rt.load_library()
+    header = open(os.path.join(REPO, "include", "apap_b200.h")).read()
+    declared = set(re.findall(r"\b(apap_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(rt.SIGNATURES), declared ^ set(rt.SIGNATURES)
+    raw = ctypes.CDLL(rt.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert lib.apap_abi_version() == 1
+    m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
+    assert int(m.group(1)) == rt.KP_ROW
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    import torch
+    if not torch.cuda.is_available():
+        st = APAP(0.5, 100, [64, 48], [0, 0])
+        sc = synth.make_scene("tiny")
+        with pytest.raises(rt.ApapError):
+            st.local_homography(sc.src, sc.dst, sc.vertices)
+        with pytest.raises(rt.ApapError):
+            apap_utils.uniform_blend(np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4, 3), np.uint8))
+    pkg = os.path.join(REPO, "cvx_proj_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert not re.search(r"""["']/root/reference""", text), f     # citations in docstrings are fine
+
+
+def test_shard_plan_tiles_canvas():
+    sc = synth.make_scene("c1")
+    col, row = papap.cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, sc.mesh_cells, sc.mesh_cells)
+    for world in (1, 2, 3, 4, 8):
+        shards = sharding.plan_shards(row, sc.mesh_cells, world)
+        assert shards[0].cell_row0 == 0 and shards[-1].cell_row1 == sc.mesh_cells
+        assert shards[0].px_row0 == 0 and shards[-1].px_row1 == sc.final_h
+        for a, b in zip(shards, shards[1:]):
+            assert a.cell_row1 == b.cell_row0 and a.px_row1 == b.px_row0
+        for s in shards:
+            assert set(np.unique(row[s.px_row0:s.px_row1])) <= set(range(s.cell_row0, s.cell_row1))
+        sizes = [s.n_cell_rows for s in shards]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {repo!r})
+import numpy as np, torch, torch.distributed as dist
+from cvx_proj_b200 import sharding, synth
+from cvx_proj_b200.apap import cell_lookup_tables
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sc = synth.make_scene("mini")
+col, row = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, sc.mesh_cells, sc.mesh_cells)
+shards = sharding.plan_shards(row, sc.mesh_cells, world)
+rng = np.random.default_rng(5)
+full = rng.integers(0, 256, size=(sc.final_h, sc.final_w, 3), dtype=np.uint8)     # same on every rank
+me = shards[rank]
+band = torch.from_numpy(full[me.px_row0:me.px_row1].copy())
+pano = sharding.gather_bands(band, shards, sc.final_w)
+assert pano.shape == (sc.final_h, sc.final_w, 3), pano.shape
+assert np.array_equal(pano.numpy(), full)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_band_gather_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(repo=REPO))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
