@@ -205,7 +205,7 @@ class Pass:
     def __init__(self, torch, device, name, seed=0, rows=None):
         from cvx_proj_b200 import synth
         from cvx_proj_b200 import _runtime as rt
-        from cvx_proj_b200.apap import APAP, cell_lookup_tables
+        from cvx_proj_b200.apap import APAP, cell_lookup_tables, scale_anchors, weight_scale
         self.torch, self.device, self.rt = torch, device, rt
         self.sc = sc = synth.make_scene(name, seed=seed)
         self.st = APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y], device=device)
@@ -217,30 +217,30 @@ class Pass:
         table, tmats = self.st._prepare(sc.src, sc.dst)
         self.n_pad = table.shape[0]
         self.table = torch.from_numpy(table).to(device)
-        self.anchors = torch.from_numpy(verts.reshape(-1, 2).astype(np.float32)).to(device)
+        self.anchors = torch.from_numpy(scale_anchors(verts, weight_scale(sc.sigma))).to(device)
         self.tmats = torch.from_numpy(tmats).to(device)
         self.k_splits, self.cells_padded, nbytes = rt.gram_plan(self.cells, self.n_pad)
         self.partials = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
         self.h_out = torch.empty((self.cells, 9), dtype=torch.float32, device=device)
-        self.k2, self.g2 = (float(v) for v in self.st._kernel_scalars())
+        self.g2 = float(np.float32(float(sc.gamma) ** 2))
         self.col_cell, self.row_cell = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, m, m)
         self.stream = rt.stream_ptr(torch, device)
 
     # -- moving DLT
     def gram(self):
         self.rt.check(self.lib.apap_gram_partials(self.table.data_ptr(), self.anchors.data_ptr(), 1, self.cells,
-                                                  self.n_pad, self.k2, self.g2, self.partials.data_ptr(),
+                                                  self.n_pad, self.g2, self.partials.data_ptr(),
                                                   self.stream), "gram")
 
     def eig(self):
         self.rt.check(self.lib.apap_eig_denorm(self.partials.data_ptr(), self.tmats.data_ptr(), 1, self.cells,
-                                               self.n_pad, self.h_out.data_ptr(), None, self.stream), "eig")
+                                               self.n_pad, self.rt.EIG_AUTO, self.h_out.data_ptr(), None, self.stream),
+                      "eig")
 
     # -- warp
     def prepare_warp(self, px_rows=None):
         """Upload the image, the inverted grid rows and the lookup tables (outside the timed region)."""
         from cvx_proj_b200 import synth
-        from cvx_proj_b200.apap import build_hinv_rows
         torch, sc = self.torch, self.sc
         self.torch.cuda.synchronize()
         m = sc.mesh_cells
@@ -249,13 +249,10 @@ class Pass:
         inv = np.linalg.inv(h).astype(np.float32)
         img = sc.image(1)
         centre = synth.make_image(sc.width, sc.height, seed=2)
-        rows = build_hinv_rows(inv, self.col_cell, self.row_cell, sc.offset_x, sc.offset_y, sc.width, sc.height)
-        self.flagged_cells = float((rows[:, 9] >= 1).mean())
+        self.tables = self.st.warp_tables_device(inv, self.col_cell, self.row_cell, sc.width, sc.height, self.device)
+        self.flagged_cells = self.tables.exact_cells_frac
         self.img = torch.from_numpy(img).to(self.device)
         self.centre = torch.from_numpy(centre).to(self.device)
-        self.rows_dev = torch.from_numpy(rows).to(self.device)
-        self.col_dev = torch.from_numpy(self.col_cell).to(self.device)
-        self.row_dev = torch.from_numpy(self.row_cell).to(self.device)
         self.px_rows = px_rows if px_rows is not None else (0, sc.final_h)
         n = self.px_rows[1] - self.px_rows[0]
         self.canvas = torch.empty((n, sc.final_w, 3), dtype=torch.uint8, device=self.device)
@@ -264,8 +261,7 @@ class Pass:
         self.host_img, self.host_centre = img, centre
 
     def warp(self, fused=False):
-        self.st.warp_device(self.img, self.rows_dev, self.col_dev, self.row_dev, self.sc.mesh_cells,
-                            self.px_rows[0], self.px_rows[1], centre_dev=self.centre if fused else None,
+        self.st.warp_device(self.img, self.tables, self.sc.mesh_cells, self.px_rows[0], self.px_rows[1], centre_dev=self.centre if fused else None,
                             out=self.canvas)
 
     def blend(self):

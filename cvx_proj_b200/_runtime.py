@@ -17,7 +17,9 @@ GRAM_TERMS = 24
 KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
-ABI_VERSION = 1
+ABI_VERSION = 2
+EIG_AUTO = 0
+EIG_JACOBI = 1
 
 # symbol -> (restype, argtypes); tests check every symbol of include/apap_b200.h is exported
 SIGNATURES = {
@@ -25,13 +27,13 @@ SIGNATURES = {
     "apap_last_error": (c_char_p, []),
     "apap_device_sm_count": (c_int, [POINTER(c_int)]),
     "apap_gram_plan": (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
-    "apap_gram_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
-    "apap_eig_denorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+    "apap_gram_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "apap_eig_denorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "apap_local_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
-    "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                          c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                          c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "apap_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "apap_fp32_probe": (c_int, [c_int, c_void_p, POINTER(c_double), c_void_p]),
 }

@@ -20,23 +20,32 @@ from __future__ import annotations
 
 import ctypes
 import math
+from typing import NamedTuple
 
 import numpy as np
 
 from . import _runtime as rt
 from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW
 
-__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "expand_gram", "build_hinv_rows", "cell_lookup_tables"]
+__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "cell_lookup_tables"]
 
 _U = 2.0 ** -24          # float32 unit roundoff
 
 
 # ------------------------------------------------------------------------------ host helpers
-def build_kp_table(src_point: np.ndarray, dlt: np.ndarray) -> np.ndarray:
+def weight_scale(sigma) -> float:
+    """``s = 2 log2(e) / sigma^2``: with coordinates multiplied by s, the squared moving-DLT weight
+    ``max(exp(-|v - x| / sigma^2), gamma)^2`` (pyviz/apap.py:142,150-152) is ``max(2^-|s v - s x|, gamma^2)``."""
+    return 2.0 * math.log2(math.e) / (float(sigma) ** 2)
+
+
+def build_kp_table(src_point: np.ndarray, dlt: np.ndarray, scale: float) -> np.ndarray:
     """Keypoint table of the Gram kernel: ``[N_padded, 28]`` float32.
 
-    Row i = the 24 distinct non-zero sums' per-keypoint terms, then the raw keypoint
-    (kx, ky) the weight is measured from, then 2 floats of padding (112 B, 16-B aligned).
+    Row i = the 24 distinct non-zero sums' per-keypoint terms, then the raw keypoint the weight
+    is measured from, pre-scaled by ``scale`` (``weight_scale(sigma)``) and with each coordinate
+    stored twice -- ``s kx, s kx, s ky, s ky`` -- the operand layout of the kernel's packed FP32
+    arithmetic (112 B per row, 16-B aligned).
     With ``m = [x, y, 1]`` (conditioned source point) and ``(x', y')`` the conditioned target,
     the Gram matrix of the two DLT rows (pyviz/apap.py:106-118) is
     ``[[S, 0, -Sx], [0, S, -Sy], [-Sx, -Sy, Sr]]`` with ``S = m m^T``, ``Sx = x' m m^T``,
@@ -55,8 +64,15 @@ def build_kp_table(src_point: np.ndarray, dlt: np.ndarray) -> np.ndarray:
     tab[:n, 6:12] = xp[:, None] * m
     tab[:n, 12:18] = yp[:, None] * m
     tab[:n, 18:24] = (xp * xp + yp * yp)[:, None] * m
-    tab[:n, 24:26] = src_point
+    scaled = src_point.astype(np.float64) * scale
+    tab[:n, 24:26] = scaled[:, 0:1]
+    tab[:n, 26:28] = scaled[:, 1:2]
     return tab
+
+
+def scale_anchors(vertices, scale: float) -> np.ndarray:
+    """``[..., 2]`` float64 cell anchors (``get_vertice``) -> ``[cells, 2]`` float32, pre-scaled."""
+    return (np.asarray(vertices, dtype=np.float64).reshape(-1, 2) * scale).astype(np.float32)
 
 
 _SYM3 = np.array([[0, 1, 2], [1, 3, 4], [2, 4, 5]])
@@ -98,60 +114,143 @@ def cell_lookup_tables(mesh: np.ndarray, final_w: int, final_h: int, grid_rows: 
     return out[0], out[1]
 
 
-def build_hinv_rows(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndarray, off_x: int, off_y: int,
-                    src_w: int, src_h: int) -> np.ndarray:
-    """Per-cell rows of the warp kernel: ``[rows*cols, 12]`` float32 = 9 entries of H^-1,
-    ``eps_x``, ``eps_y``, pad.
+_MAGIC_BITS = 0x4B400000        # float32 bits of 1.5 * 2**23 (kMagic of csrc/warp_blend.cu)
 
-    ``eps`` is a rigorous bound on the absolute error of the kernel's float32 source coordinate
-    inside the cell's pixel rectangle (two fused multiply-adds per numerator, reciprocal +
-    residual-corrected quotient).  A coordinate farther than eps from every integer gets the same
-    floor and bounds decision in float32 as in the reference's float64; the kernel recomputes the
-    others in float64.  ``eps = 1`` sends the whole cell to the float64 path (denominator changes
-    sign or comes close to zero inside the cell).
+
+def _cell_extent(lut: np.ndarray, n: int):
+    """Per cell index: smallest / largest pixel coordinate mapped to it (lo > hi = unused)."""
+    lo = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+    hi = np.full(n, np.iinfo(np.int64).min, dtype=np.int64)
+    k = np.arange(lut.shape[0], dtype=np.int64)
+    np.minimum.at(lo, lut, k)
+    np.maximum.at(hi, lut, k)
+    return lo, hi
+
+
+def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndarray, off_x: int, off_y: int,
+                      src_w: int, src_h: int):
+    """Kernel inputs of the mesh warp: ``(cell_fast[cells, 12] f32, col_lut[W, 2] u32, row_lut[H, 2] u32)``.
+
+    ``col_lut[j] = (cell column, float32 bits of dx)`` with ``dx = j - (first canvas column of that
+    cell)``; ``row_lut`` likewise.  ``cell_fast`` holds, per cell, the float32 fast path of
+    ``csrc/warp_blend.cu``: with ``(x0, y0)`` the cell's first pixel minus the canvas offsets, the
+    reference's ``t = H^-1 [x0 + dx, y0 + dy, 1]`` (pyviz/apap.py:211-213) is rewritten as
+
+        t_x / t_z - qbx = (A0 dx + B0 dy + C0) / (A2 dx + B2 dy + C2)        (same for y with A1 B1 C1, qby)
+
+    where ``(qbx, qby)`` is the integer source position of the cell centre and everything is scaled
+    so the denominator is ~1.  Layout: ``A0 B0 C0 A1 | B1 C1 A2 B2 | C2, int32 bits of qbx - 0x4B400000,
+    of qby - 0x4B400000, 0.5 - eps``.  ``eps`` is a rigorous bound on the absolute error of the
+    kernel's float32 quotient inside the cell (coefficient rounding, two fused multiply-adds per
+    numerator, ``rcp.approx`` and one multiply); a quotient farther than eps from every integer
+    gets the same floor and bounds decision as the reference's float64, the kernel recomputes the
+    others in float64.  ``0.5 - eps = -1`` sends the whole cell to the float64 path (denominator
+    changes sign or varies too much inside the cell, coordinates beyond 2^20, non-finite entries).
     """
     gr, gc = inv_h.shape[0], inv_h.shape[1]
     h = inv_h.astype(np.float64).reshape(gr, gc, 9)
+    col64, row64 = col_cell.astype(np.int64), row_cell.astype(np.int64)
+    jlo, jhi = _cell_extent(col64, gc)
+    ilo, ihi = _cell_extent(row64, gr)
+    col_used, row_used = jlo <= jhi, ilo <= ihi
+    jlo, jhi = np.where(col_used, jlo, 0), np.where(col_used, jhi, 0)
+    ilo, ihi = np.where(row_used, ilo, 0), np.where(row_used, ihi, 0)
 
-    def extent(lut, n):      # per cell index: smallest / largest pixel coordinate mapped to it
-        lo = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
-        hi = np.full(n, np.iinfo(np.int64).min, dtype=np.int64)
-        k = np.arange(lut.shape[0], dtype=np.int64)
-        np.minimum.at(lo, lut, k)
-        np.maximum.at(hi, lut, k)
-        return lo, hi
+    col_lut = np.empty((col_cell.shape[0], 2), dtype=np.uint32)
+    col_lut[:, 0] = col_cell
+    col_lut[:, 1] = (np.arange(col_cell.shape[0]) - jlo[col64]).astype(np.float32).view(np.uint32)
+    row_lut = np.empty((row_cell.shape[0], 2), dtype=np.uint32)
+    row_lut[:, 0] = row_cell
+    row_lut[:, 1] = (np.arange(row_cell.shape[0]) - ilo[row64]).astype(np.float32).view(np.uint32)
 
-    jlo, jhi = extent(col_cell.astype(np.int64), gc)
-    ilo, ihi = extent(row_cell.astype(np.int64), gr)
-    used = (jlo <= jhi)[None, :] & (ilo <= ihi)[:, None]
-    xlo = np.where(jlo <= jhi, jlo - off_x, 0).astype(np.float64)[None, :]
-    xhi = np.where(jlo <= jhi, jhi - off_x, 0).astype(np.float64)[None, :]
-    ylo = np.where(ilo <= ihi, ilo - off_y, 0).astype(np.float64)[:, None]
-    yhi = np.where(ilo <= ihi, ihi - off_y, 0).astype(np.float64)[:, None]
-    xa = np.maximum(np.abs(xlo), np.abs(xhi))
-    ya = np.maximum(np.abs(ylo), np.abs(yhi))
-    ah = np.abs(h)
-    m0 = ah[..., 0] * xa + ah[..., 1] * ya + ah[..., 2]
-    m1 = ah[..., 3] * xa + ah[..., 4] * ya + ah[..., 5]
-    m2 = ah[..., 6] * xa + ah[..., 7] * ya + ah[..., 8]
-    corners = np.stack([h[..., 6] * cx + h[..., 7] * cy + h[..., 8]
-                        for cx in (xlo, xhi) for cy in (ylo, yhi)], axis=-1)
-    same_sign = (corners > 0).all(axis=-1) | (corners < 0).all(axis=-1)
-    t2min = np.abs(corners).min(axis=-1) - 4 * _U * m2            # computed |t2| is at least this
-    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-        ok = same_sign & (t2min > 0) & used
-        t2s = np.where(ok, t2min, 1.0)
-        eps = []
-        for mk, lim in ((m0, src_w + 2.0), (m1, src_h + 2.0)):
-            q = np.minimum(mk / t2s, lim)
-            e = 1.5 * ((2 * _U * mk + q * 2 * _U * m2) / t2s + 1.01 * _U * q) + 4e-6
-            eps.append(np.where(ok & np.isfinite(e) & (e < 0.25), e, 1.0))
-    rows = np.zeros((gr, gc, HINV_ROW), dtype=np.float32)
-    rows[..., 0:9] = inv_h.reshape(gr, gc, 9)
-    # round the bounds up when narrowing to float32
-    rows[..., 9] = np.nextafter(eps[0].astype(np.float32), np.float32(2))
-    rows[..., 10] = np.nextafter(eps[1].astype(np.float32), np.float32(2))
-    return rows.reshape(gr * gc, HINV_ROW)
+    x0 = (jlo - off_x).astype(np.float64)[None, :]
+    y0 = (ilo - off_y).astype(np.float64)[:, None]
+    dxm = (jhi - jlo).astype(np.float64)[None, :]
+    dym = (ihi - ilo).astype(np.float64)[:, None]
+    used = col_used[None, :] & row_used[:, None]
+    with np.errstate(all="ignore"):
+        t0 = h[..., 0] * x0 + h[..., 1] * y0 + h[..., 2]
+        t1 = h[..., 3] * x0 + h[..., 4] * y0 + h[..., 5]
+        t2 = h[..., 6] * x0 + h[..., 7] * y0 + h[..., 8]
+        # integer base: the source position of the cell centre
+        c0 = t0 + h[..., 0] * (0.5 * dxm) + h[..., 1] * (0.5 * dym)
+        c1 = t1 + h[..., 3] * (0.5 * dxm) + h[..., 4] * (0.5 * dym)
+        c2 = t2 + h[..., 6] * (0.5 * dxm) + h[..., 7] * (0.5 * dym)
+        bx, by = np.rint(c0 / c2), np.rint(c1 / c2)
+        ok = used & np.isfinite(bx) & np.isfinite(by) & (np.abs(bx) < 2.0 ** 30) & (np.abs(by) < 2.0 ** 30) & (c2 != 0)
+        bx, by = np.where(ok, bx, 0.0), np.where(ok, by, 0.0)
+        s = np.where(ok, 1.0 / np.where(ok, c2, 1.0), 0.0)
+        coef = np.stack([(h[..., 0] - bx * h[..., 6]) * s, (h[..., 1] - bx * h[..., 7]) * s, (t0 - bx * t2) * s,
+                         (h[..., 3] - by * h[..., 6]) * s, (h[..., 4] - by * h[..., 7]) * s, (t1 - by * t2) * s,
+                         h[..., 6] * s, h[..., 7] * s, t2 * s], axis=-1)
+        ok &= np.isfinite(coef).all(axis=-1)
+        coef = np.where(ok[..., None], coef, 0.0).astype(np.float32).astype(np.float64)   # what the kernel sees
+        m = [np.abs(coef[..., 3 * k]) * dxm + np.abs(coef[..., 3 * k + 1]) * dym + np.abs(coef[..., 3 * k + 2])
+             for k in range(3)]
+        corners = np.stack([coef[..., 6] * cx + coef[..., 7] * cy + coef[..., 8]
+                            for cx in (0.0 * dxm, dxm) for cy in (0.0 * dym, dym)], axis=-1)
+        same_sign = (corners > 0).all(axis=-1)
+        d_err = 3.0 * _U * m[2]
+        d_min = corners.min(axis=-1) - d_err                     # the computed denominator is at least this
+        ok &= same_sign & (d_min >= 0.25)
+        d_safe = np.where(ok, d_min, 1.0)
+        eps = np.zeros_like(d_safe)
+        for k in (0, 1):
+            q = m[k] / d_safe
+            e = (3.0 * _U * m[k] + q * d_err) / d_safe + q * (2.0 ** -22 + _U)
+            ok &= np.isfinite(q) & (q < 2.0 ** 20)
+            eps = np.maximum(eps, np.where(np.isfinite(e), e, 1.0))
+        eps = 1.25 * eps + 1e-7
+        ok &= eps < 0.25
+    rec = np.zeros((gr, gc, HINV_ROW), dtype=np.float32)
+    rec[..., 0:9] = np.where(ok[..., None], coef, 0.0)
+    rec[..., 8] = np.where(ok, rec[..., 8], 1.0)
+    bits = rec.view(np.uint32)
+    bits[..., 9] = (np.where(ok, bx, 0.0).astype(np.int64) - _MAGIC_BITS).astype(np.int32).view(np.uint32)
+    bits[..., 10] = (np.where(ok, by, 0.0).astype(np.int64) - _MAGIC_BITS).astype(np.int32).view(np.uint32)
+    hme = np.where(ok, 0.5 - eps, -1.0)
+    hme32 = hme.astype(np.float32)
+    hme32 = np.where(hme32.astype(np.float64) > hme, np.nextafter(hme32, np.float32(-2)), hme32)   # round down
+    rec[..., 11] = hme32
+    return rec.reshape(gr * gc, HINV_ROW), col_lut, row_lut
+
+
+class _PinnedStage:
+    """A reusable pinned host buffer for packing several small arrays into ONE host->device copy.
+    The copy is asynchronous; an event guards the buffer against being refilled while in flight."""
+
+    def __init__(self):
+        self.buf = None
+        self.event = None
+
+    def upload(self, torch, device, arrays):
+        """Returns one uint8 device view per array (each section starts 16-byte aligned)."""
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total = (total + a.nbytes + 15) // 16 * 16
+        if self.buf is None or self.buf.numel() < total:
+            self.buf = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self.event = None
+        if self.event is not None:
+            self.event.synchronize()
+        host = self.buf.numpy()
+        for a, off in zip(arrays, offs):
+            host[off:off + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        with torch.cuda.device(device):
+            dev = self.buf[:total].to(device, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+        return [dev[off:off + a.nbytes] for a, off in zip(arrays, offs)]
+
+
+class WarpTables(NamedTuple):
+    """Device-resident inputs of ``apap_warp`` for one inverted grid (see ``build_warp_tables``)."""
+    cell_fast: object       # float32 [cells * 12]
+    cell_hinv: object       # float32 [cells * 9]
+    col_lut: object         # int32 [canvas_w * 2]
+    row_lut: object         # int32 [canvas_h * 2]
+    exact_cells_frac: float  # share of cells whose every pixel takes the float64 path
 
 
 class LazyLocalWeight:
@@ -308,7 +407,7 @@ class APAP:
         cf1 = self.point_normalize(nf1, c1)
         cf2 = self.point_normalize(nf2, c2)
         dlt = self.matrix_generate(sample_n, cf1, cf2)
-        table = build_kp_table(src_point.astype(np.float32, copy=False), dlt)
+        table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
         # h -> inv(N2) (inv(C2) h C1) N1   (pyviz/apap.py:165-166); inverses in float32 like the reference
         t2inv = np.linalg.inv(n2).astype(np.float64) @ np.linalg.inv(c2).astype(np.float64)
         t1 = c1.astype(np.float64) @ n1.astype(np.float64)
@@ -320,30 +419,16 @@ class APAP:
         packed into a pinned staging buffer (kept per instance) and sliced on the device.
         Layout: float32 tables [b, n_pad, 28] | float32 anchors [b, cells, 2] | float64 tmats [b, 18]
         (every section starts 16-byte aligned)."""
-        sizes = [tables.nbytes, anchors.nbytes, tmats.nbytes]
-        offs = [0, (sizes[0] + 15) // 16 * 16]
-        offs.append((offs[1] + sizes[1] + 15) // 16 * 16)
-        total = offs[2] + sizes[2]
-        stage = getattr(self, "_stage", None)
-        if stage is None or stage.numel() < total or stage.device != torch.device("cpu"):
-            stage = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
-            self._stage = stage
-        host = stage.numpy()
-        for arr, off, nb in zip((tables, anchors, tmats), offs, sizes):
-            host[off:off + nb] = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
-        dev = stage[:total].to(device, non_blocking=True)
-        t_dev = dev[offs[0]:offs[0] + sizes[0]].view(torch.float32).view(tables.shape)
-        a_dev = dev[offs[1]:offs[1] + sizes[1]].view(torch.float32).view(anchors.shape)
-        m_dev = dev[offs[2]:offs[2] + sizes[2]].view(torch.float64).view(tmats.shape)
-        return t_dev, a_dev, m_dev
-
-    def _kernel_scalars(self):
-        k2 = -2.0 * math.log2(math.e) / (float(self.sigma) ** 2)
-        return np.float32(k2), np.float32(float(self.gamma) ** 2)
+        if not hasattr(self, "_stage"):
+            self._stage = _PinnedStage()
+        t_u8, a_u8, m_u8 = self._stage.upload(torch, device, (tables, anchors, tmats))
+        return (t_u8.view(torch.float32).view(tables.shape), a_u8.view(torch.float32).view(anchors.shape),
+                m_u8.view(torch.float64).view(tmats.shape))
 
     def local_homography_device(self, table_dev, anchors_dev, tmats_dev, batch, cells, out_h=None, partials=None,
-                                sweeps=None):
-        """Device-resident K1 + K2 (no host traffic): tensors in, ``[batch, cells, 9]`` float32 out."""
+                                sweeps=None, solver=rt.EIG_AUTO):
+        """Device-resident K1 + K2 (no host traffic): tensors in, ``[batch, cells, 9]`` float32 out.
+        ``table_dev`` / ``anchors_dev`` hold pre-scaled coordinates (``build_kp_table``, ``scale_anchors``)."""
         torch, device = rt.torch_cuda(table_dev.device)
         lib = rt.load_library()
         n_pad = table_dev.shape[-2]
@@ -352,11 +437,10 @@ class APAP:
             partials = torch.empty(batch * nbytes // 4, dtype=torch.float32, device=device)
         if out_h is None:
             out_h = torch.empty((batch, cells, 9), dtype=torch.float32, device=device)
-        k2, g2 = self._kernel_scalars()
         with torch.cuda.device(device):
             rt.check(lib.apap_local_homography(
                 table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
-                float(k2), float(g2), partials.data_ptr(), out_h.data_ptr(),
+                float(np.float32(float(self.gamma) ** 2)), int(solver), partials.data_ptr(), out_h.data_ptr(),
                 sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
                 "apap_local_homography")
         return out_h
@@ -373,7 +457,7 @@ class APAP:
         table, tmats = self._prepare(src_point, dst_point)
         torch, device = rt.torch_cuda(self.device)
         cells = mesh_n * pt_size
-        anchors = np.asarray(vertices, dtype=np.float64).reshape(cells, 2).astype(np.float32)
+        anchors = scale_anchors(vertices, weight_scale(self.sigma))
         t_dev, a_dev, m_dev = self._upload_scene(torch, device, table[None], anchors[None], tmats[None])
         h_dev = self.local_homography_device(t_dev, a_dev, m_dev, 1, cells)
         h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
@@ -394,7 +478,7 @@ class APAP:
         for k, (t, _) in enumerate(prepared):
             tables[k, :t.shape[0]] = t
         tmats = np.stack([m for _, m in prepared])
-        anchors = np.stack([np.asarray(v, dtype=np.float64).reshape(cells, 2).astype(np.float32) for v in verts])
+        anchors = np.stack([scale_anchors(v, weight_scale(self.sigma)) for v in verts])
         torch, device = rt.torch_cuda(self.device)
         t_dev, a_dev, m_dev = self._upload_scene(torch, device, tables, anchors, tmats)
         h_dev = self.local_homography_device(t_dev, a_dev, m_dev, count, cells)
@@ -411,8 +495,22 @@ class APAP:
             self._lut_cache = {key: hit}
         return hit
 
-    def warp_device(self, src_dev, rows_dev, col_dev, row_dev, grid_cols, row0=0, row1=None, centre_dev=None,
-                    out=None, force_exact=False):
+    def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None):
+        """Build the warp kernel's tables (``build_warp_tables``) for an inverted grid and upload them
+        with one host->device copy.  Returns ``WarpTables`` (device tensors)."""
+        torch, device = rt.torch_cuda(device if device is not None else self.device)
+        fast, col_lut, row_lut = build_warp_tables(inv_h, col_cell, row_cell, int(self.offset_x), int(self.offset_y),
+                                                   int(src_w), int(src_h))
+        hinv = np.ascontiguousarray(inv_h, dtype=np.float32).reshape(-1, 9)
+        if not hasattr(self, "_warp_stage"):
+            self._warp_stage = _PinnedStage()
+        views = self._warp_stage.upload(torch, device, (fast, hinv, col_lut, row_lut))
+        return WarpTables(views[0].view(torch.float32), views[1].view(torch.float32),
+                          views[2].view(torch.int32), views[3].view(torch.int32),
+                          float((fast[:, 11] < 0).mean()))
+
+    def warp_device(self, src_dev, tables, grid_cols, row0=0, row1=None, centre_dev=None, out=None,
+                    force_exact=False):
         """Device-resident K3 (optionally fused with K4): writes canvas rows ``[row0, row1)`` into
         ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None)."""
         torch, device = rt.torch_cuda(src_dev.device)
@@ -424,8 +522,9 @@ class APAP:
         ch, cw = (centre_dev.shape[0], centre_dev.shape[1]) if centre_dev is not None else (0, 0)
         with torch.cuda.device(device):
             rt.check(lib.apap_warp(
-                src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], rows_dev.data_ptr(), col_dev.data_ptr(),
-                row_dev.data_ptr(), grid_cols, fw, fh, int(self.offset_x), int(self.offset_y), row0, row1,
+                src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
+                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_lut.data_ptr(), grid_cols, fw, fh,
+                int(self.offset_x), int(self.offset_y), row0, row1,
                 centre_dev.data_ptr() if centre_dev is not None else None, ch, cw, out.data_ptr(),
                 1 if force_exact else 0, rt.stream_ptr(torch, device)), "apap_warp")
         return out
@@ -436,8 +535,6 @@ class APAP:
         # in-place per-cell inverse, stored back in the caller's array (pyviz/apap.py:201-203)
         local_homography[...] = np.linalg.inv(local_homography)
         col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
-        rows = build_hinv_rows(local_homography, col_cell, row_cell, int(self.offset_x), int(self.offset_y),
-                               int(ori_w), int(ori_h))
         on_device = not isinstance(ori_img, np.ndarray)
         torch, device = rt.torch_cuda(ori_img.device if on_device else self.device)
         src_dev = ori_img.contiguous() if on_device else rt.to_device(torch, device, ori_img.astype(np.uint8, copy=False))
@@ -445,9 +542,8 @@ class APAP:
         if centre_img is not None:
             centre_dev = (centre_img.contiguous() if not isinstance(centre_img, np.ndarray)
                           else rt.to_device(torch, device, centre_img.astype(np.uint8, copy=False)))
-        out = self.warp_device(src_dev, rt.to_device(torch, device, rows), rt.to_device(torch, device, col_cell),
-                               rt.to_device(torch, device, row_cell), pt_size, centre_dev=centre_dev,
-                               force_exact=force_exact)
+        tables = self.warp_tables_device(local_homography, col_cell, row_cell, ori_w, ori_h, device)
+        out = self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)
         return out if on_device else rt.to_host(torch, out)
 
     def local_warp(self, ori_img, local_homography, mesh, progress=False):

@@ -58,28 +58,29 @@ int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
 }
 
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
-                       float neg2_log2e_inv_sigma_sq, float gamma_sq, float *partials, void *stream) {
+                       float gamma_sq, float *partials, void *stream) {
   int rc = check_table(kp_table, anchors, batch, cells, n_kp_padded);
   if (rc) return rc;
   if (!partials) return fail(APAP_E_BADARG, "null partials");
-  return launch_gram(kp_table, anchors, batch, cells, n_kp_padded, neg2_log2e_inv_sigma_sq, gamma_sq, partials,
+  return launch_gram(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials,
                      static_cast<cudaStream_t>(stream));
 }
 
-int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded, float *out_h,
-                    int *out_sweeps, void *stream) {
+int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded, int solver,
+                    float *out_h, int *out_sweeps, void *stream) {
   if (!partials || !tmats || !out_h) return fail(APAP_E_BADARG, "null pointer");
   if (batch <= 0 || cells <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "eig: bad sizes");
-  return launch_eig(partials, tmats, batch, cells, n_kp_padded, out_h, out_sweeps, static_cast<cudaStream_t>(stream));
+  if (solver != APAP_EIG_AUTO && solver != APAP_EIG_JACOBI) return fail(APAP_E_BADARG, "eig: unknown solver");
+  return launch_eig(partials, tmats, batch, cells, n_kp_padded, out_h, out_sweeps, solver == APAP_EIG_JACOBI,
+                    static_cast<cudaStream_t>(stream));
 }
 
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats, int batch, int cells,
-                          int n_kp_padded, float neg2_log2e_inv_sigma_sq, float gamma_sq, float *partials,
-                          float *out_h, int *out_sweeps, void *stream) {
-  int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, neg2_log2e_inv_sigma_sq, gamma_sq,
-                              partials, stream);
+                          int n_kp_padded, float gamma_sq, int solver,
+                          float *partials, float *out_h, int *out_sweeps, void *stream) {
+  int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials, stream);
   if (rc) return rc;
-  return apap_eig_denorm(partials, tmats, batch, cells, n_kp_padded, out_h, out_sweeps, stream);
+  return apap_eig_denorm(partials, tmats, batch, cells, n_kp_padded, solver, out_h, out_sweeps, stream);
 }
 
 int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
@@ -89,16 +90,17 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
   return launch_weight(anchors, kp_xy, cells, n_kp, inv_sigma_sq, gamma, out, static_cast<cudaStream_t>(stream));
 }
 
-int apap_warp(const uint8_t *src, int src_h, int src_w, const float *hinv, const uint16_t *col_cell,
-              const uint16_t *row_cell, int grid_cols, int canvas_w, int canvas_h, int off_x, int off_y, int row0,
-              int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band, int force_exact,
-              void *stream) {
-  if (!src || !hinv || !col_cell || !row_cell || !out_band) return fail(APAP_E_BADARG, "null pointer");
+int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
+              const uint32_t *col_lut, const uint32_t *row_lut, int grid_cols, int canvas_w, int canvas_h, int off_x,
+              int off_y, int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
+              int force_exact, void *stream) {
+  if (!src || !cell_fast || !cell_hinv || !col_lut || !row_lut || !out_band) return fail(APAP_E_BADARG, "null pointer");
   if (src_h <= 0 || src_w <= 0 || canvas_w <= 0 || canvas_h <= 0 || grid_cols <= 0)
     return fail(APAP_E_BADARG, "warp: sizes must be > 0");
   if (centre && (centre_h <= 0 || centre_w <= 0)) return fail(APAP_E_BADARG, "warp: bad centre image size");
-  return launch_warp(src, src_h, src_w, hinv, col_cell, row_cell, grid_cols, canvas_w, canvas_h, off_x, off_y, row0,
-                     row1, centre, centre_h, centre_w, out_band, force_exact, static_cast<cudaStream_t>(stream));
+  return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, row_lut, grid_cols, canvas_w, canvas_h, off_x,
+                     off_y, row0, row1, centre, centre_h, centre_w, out_band, force_exact,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream) {

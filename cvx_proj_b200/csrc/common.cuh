@@ -22,8 +22,8 @@ constexpr int kMaxChainChunks = 8;          // 8 x 128 = 1024 keypoints per spli
 struct GramPlan {
   int k_splits;
   int chunks_per_split;
-  int cells_per_thread;     // register tile: cells handled by one thread (1, 2 or 4)
-  int cells_padded;         // multiple of 128 * cells_per_thread
+  int cells_per_thread;     // register tile: cells handled by one thread
+  int cells_padded;         // row pitch of the partial sums (multiple of 512)
   int cell_tiles;
 };
 
@@ -36,14 +36,14 @@ int check_cuda(cudaError_t e, const char *what);
 
 // launchers (one per translation unit)
 int launch_gram(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
-                float k2, float gamma_sq, float *partials, cudaStream_t st);
+                float gamma_sq, float *partials, cudaStream_t st);
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded,
-               float *out_h, int *out_sweeps, cudaStream_t st);
+               float *out_h, int *out_sweeps, int force_jacobi, cudaStream_t st);
 int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
                   double gamma, double *out, cudaStream_t st);
-int launch_warp(const uint8_t *src, int src_h, int src_w, const float *hinv, const uint16_t *col_cell,
-                const uint16_t *row_cell, int grid_cols, int canvas_w, int canvas_h, int off_x, int off_y,
-                int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
+int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
+                const uint32_t *col_lut, const uint32_t *row_lut, int grid_cols, int canvas_w, int canvas_h, int off_x,
+                int off_y, int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
                 int force_exact, cudaStream_t st);
 int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, cudaStream_t st);
 int launch_probe(int iters, float *sink, double *flops, cudaStream_t st);

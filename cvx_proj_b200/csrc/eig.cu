@@ -1,19 +1,24 @@
 // K2 -- batched 9x9 symmetric eigensolve + de-normalisation
 // (reference pyviz/apap.py:160-161 cv.SVDecomp + V[-1], and :164-168).
 //
-// One thread per cell: the 45 upper-triangle entries of the Gram matrix and the 81 entries of
-// the eigenvector matrix live in registers (every index is a compile-time constant after
-// unrolling), so a warp solves 32 cells with no shuffles or shared memory.  The k_splits FP32
-// partial sums of K1 are combined in float64 in a fixed order, scaled by 1/sum(w^2) and
-// diagonalised by cyclic Jacobi in FP32 with the relative rotation threshold
-// |g_pq| <= eps * sqrt(g_pp g_qq) (so small eigenvalues keep their relative accuracy).  The
-// eigenvector of the smallest eigenvalue is de-normalised in float64 and stored as float32.
+// One thread per cell, everything in registers (every index is a compile-time constant after
+// unrolling).  The k_splits FP32 partial sums of K1 are combined in float64 in a fixed order and
+// scaled by 1/sum(w^2).  The wanted vector -- the right singular vector of the weighted DLT
+// matrix for its smallest singular value -- is the eigenvector of the smallest eigenvalue of the
+// 9x9 Gram matrix.  That eigenvalue is separated from the next one by 4-6 orders of magnitude
+// on real data, so the fast path is float64 inverse iteration on an LDL^T
+// factorisation (~0.5 kflop per cell, settles in 2-3 steps).  A cell whose iteration has not
+// settled after kMaxInvIter steps (tiny spectral gap: degenerate keypoint sets) falls back to
+// the full cyclic Jacobi diagonalisation in FP32 with the relative rotation threshold
+// |g_pq| <= eps * sqrt(g_pp g_qq).  The eigenvector is de-normalised in float64 and stored as
+// float32.
 #include "common.cuh"
 
 namespace apap {
 
 constexpr int kEigThreads = 128;
 constexpr int kMaxSweeps = 12;
+constexpr int kMaxInvIter = 8;
 
 __host__ __device__ constexpr int tri(int i, int j) {   // index into the packed upper triangle
   return i <= j ? (i * (19 - i)) / 2 + (j - i) : (j * (19 - j)) / 2 + (i - j);
@@ -23,6 +28,67 @@ __host__ __device__ constexpr int sym3(int a, int b) {
   return a <= b ? (a == 0 ? b : (a == 1 ? 2 + b : 5)) : sym3(b, a);
 }
 
+// ------------------------------------------------------------------------- shared pieces
+// Combine the k_splits FP32 partial sums of one cell in float64 (fixed order -> deterministic).
+__device__ __forceinline__ void combine_partials(const float *__restrict__ partials, int cells_padded, int k_splits,
+                                                 int cell, double (&sum)[kTerms]) {
+#pragma unroll
+  for (int t = 0; t < kTerms; ++t) sum[t] = 0.0;
+  for (int s = 0; s < k_splits; ++s) {
+    const float *src = partials + (size_t)s * kTerms * cells_padded + cell;
+#pragma unroll
+    for (int t = 0; t < kTerms; ++t) sum[t] += (double)__ldg(src + (size_t)t * cells_padded);
+  }
+}
+
+// Packed 9x9 Gram matrix [[S,0,-Sx],[0,S,-Sy],[-Sx,-Sy,Sr]] / sum(w^2) from the 24 sums.
+template <typename T>
+__device__ __forceinline__ void expand_gram(const double (&sum)[kTerms], T (&g)[45]) {
+  const double inv_w = 1.0 / sum[5];   // sum of w^2 > 0 (gamma > 0 or any finite weight)
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int k = sym3(a, b);
+      if (a <= b) {
+        g[tri(a, b)] = (T)(sum[k] * inv_w);
+        g[tri(3 + a, 3 + b)] = (T)(sum[k] * inv_w);
+        g[tri(6 + a, 6 + b)] = (T)(sum[18 + k] * inv_w);
+      }
+      g[tri(a, 3 + b)] = (T)0;
+      g[tri(a, 6 + b)] = (T)(-sum[6 + k] * inv_w);
+      g[tri(3 + a, 6 + b)] = (T)(-sum[12 + k] * inv_w);
+    }
+  }
+}
+
+// H = T2inv * reshape(h, 3, 3) * T1, divided by H[2][2]  (float64, stored float32; pyviz/apap.py:164-168)
+__device__ __forceinline__ void denorm_store(const double (&h)[9], const double *__restrict__ tmats,
+                                             float *__restrict__ dst) {
+  double t2[9], t1[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    t2[i] = tmats[i];
+    t1[i] = tmats[9 + i];
+  }
+  double m[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      m[r * 3 + c] = t2[r * 3 + 0] * h[0 * 3 + c] + t2[r * 3 + 1] * h[1 * 3 + c] + t2[r * 3 + 2] * h[2 * 3 + c];
+  double o[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      o[r * 3 + c] = m[r * 3 + 0] * t1[0 * 3 + c] + m[r * 3 + 1] * t1[1 * 3 + c] + m[r * 3 + 2] * t1[2 * 3 + c];
+  const double inv22 = 1.0 / o[8];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dst[i] = (float)(o[i] * inv22);
+}
+
+// ------------------------------------------------------------------ fallback: cyclic Jacobi
 template <int P, int Q>
 __device__ __forceinline__ bool rotate(float (&g)[45], float (&v)[81]) {
   const float apq = g[tri(P, Q)];
@@ -73,55 +139,24 @@ struct Sweep<8, 9> {
   __device__ __forceinline__ static bool run(float (&)[45], float (&)[81]) { return false; }
 };
 
-__global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ partials,
-                                                      const double *__restrict__ tmats, int cells,
-                                                      int cells_padded, int k_splits,
-                                                      float *__restrict__ out_h, int *__restrict__ out_sweeps) {
-  const int cell = blockIdx.x * kEigThreads + threadIdx.x;
-  const int scene = blockIdx.y;
-  if (cell >= cells) return;
-  partials += (size_t)scene * k_splits * kTerms * cells_padded;
-  tmats += (size_t)scene * 18;
-
-  // ---- combine the split partials in float64 (fixed order -> deterministic) -----------------
-  double sum[kTerms];
-#pragma unroll
-  for (int t = 0; t < kTerms; ++t) sum[t] = 0.0;
-  for (int s = 0; s < k_splits; ++s) {
-    const float *src = partials + (size_t)s * kTerms * cells_padded + cell;
-#pragma unroll
-    for (int t = 0; t < kTerms; ++t) sum[t] += (double)__ldg(src + (size_t)t * cells_padded);
-  }
-  const double inv_w = 1.0 / sum[5];   // sum of w^2 > 0 (gamma > 0 or any finite weight)
-
-  // ---- expand to the packed 9x9:  [[S,0,-Sx],[0,S,-Sy],[-Sx,-Sy,Sr]] ------------------------
+// One cell by full diagonalisation, then de-normalise and store.  Self-contained (re-reads the
+// partials) so the fast path of k_eig keeps its matrix in registers.
+__device__ __noinline__ void eig_cell_jacobi(const float *__restrict__ partials, const double *__restrict__ tmats,
+                                             int cells_padded, int k_splits, int cell, float *__restrict__ dst,
+                                             int *__restrict__ sweeps_out) {
   float g[45];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int k = sym3(a, b);
-      if (a <= b) {
-        g[tri(a, b)] = (float)(sum[k] * inv_w);
-        g[tri(3 + a, 3 + b)] = (float)(sum[k] * inv_w);
-        g[tri(6 + a, 6 + b)] = (float)(sum[18 + k] * inv_w);
-      }
-      g[tri(a, 3 + b)] = 0.f;
-      g[tri(a, 6 + b)] = (float)(-sum[6 + k] * inv_w);
-      g[tri(3 + a, 6 + b)] = (float)(-sum[12 + k] * inv_w);
-    }
+  {
+    double sum[kTerms];
+    combine_partials(partials, cells_padded, k_splits, cell, sum);
+    expand_gram(sum, g);
   }
   float v[81];
 #pragma unroll
   for (int i = 0; i < 81; ++i) v[i] = (i / 9 == i % 9) ? 1.f : 0.f;
-
-  // ---- cyclic Jacobi ------------------------------------------------------------------------
   int sweeps = 0;
   for (; sweeps < kMaxSweeps; ++sweeps) {
     if (!Sweep<0, 1>::run(g, v)) break;
   }
-
-  // ---- eigenvector of the smallest eigenvalue -------------------------------------------------
   int kmin = 0;
   float lmin = g[tri(0, 0)];
 #pragma unroll
@@ -140,39 +175,115 @@ __global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ p
     for (int k = 1; k < 9; ++k) x = (kmin == k) ? v[r * 9 + k] : x;
     h[r] = (double)x;
   }
+  denorm_store(h, tmats, dst);
+  if (sweeps_out) *sweeps_out = sweeps;
+}
 
-  // ---- H = T2inv * reshape(h, 3, 3) * T1, divided by H[2][2]  (float64, stored float32) -------
-  double t2[9], t1[9];
+// ------------------------------------------------------- fast path: LDL^T inverse iteration
+// In-place LDL^T of the packed symmetric matrix: afterwards a[tri(j,j)] = d_j, inv_d[j] = 1/d_j
+// and, for i > j, a[tri(j,i)] = l_ij.  Pivots are floored at floor_d so a singular Gram matrix
+// (exact-homography data) still yields a usable factorisation for inverse iteration.
+__device__ __forceinline__ void ldlt9(double (&a)[45], double (&inv_d)[9], double floor_d) {
 #pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    t2[i] = tmats[i];
-    t1[i] = tmats[9 + i];
+  for (int j = 0; j < 9; ++j) {
+    double t[9];                                     // t_k = l_jk d_k
+    double d = a[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) {
+      t[k] = a[tri(k, j)] * a[tri(k, k)];
+      d = fma(-a[tri(k, j)], t[k], d);
+    }
+    d = fmax(d, floor_d);
+    a[tri(j, j)] = d;
+    const double r = 1.0 / d;
+    inv_d[j] = r;
+#pragma unroll
+    for (int i = j + 1; i < 9; ++i) {
+      double s = a[tri(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fma(-a[tri(k, i)], t[k], s);
+      a[tri(j, i)] = s * r;
+    }
   }
-  double m[9];
+}
+
+// x <- (L D L^T)^-1 x
+__device__ __forceinline__ void ldlt9_solve(const double (&a)[45], const double (&inv_d)[9], double (&x)[9]) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int i = 1; i < 9; ++i)
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      m[r * 3 + c] = t2[r * 3 + 0] * h[0 * 3 + c] + t2[r * 3 + 1] * h[1 * 3 + c] + t2[r * 3 + 2] * h[2 * 3 + c];
-  double o[9];
+    for (int k = 0; k < i; ++k) x[i] = fma(-a[tri(k, i)], x[k], x[i]);
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int i = 0; i < 9; ++i) x[i] *= inv_d[i];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      o[r * 3 + c] = m[r * 3 + 0] * t1[0 * 3 + c] + m[r * 3 + 1] * t1[1 * 3 + c] + m[r * 3 + 2] * t1[2 * 3 + c];
-  const double inv22 = 1.0 / o[8];
+  for (int i = 7; i >= 0; --i)
+#pragma unroll
+    for (int k = i + 1; k < 9; ++k) x[i] = fma(-a[tri(i, k)], x[k], x[i]);
+}
+
+__global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ partials,
+                                                      const double *__restrict__ tmats, int cells,
+                                                      int cells_padded, int k_splits, int force_jacobi,
+                                                      float *__restrict__ out_h, int *__restrict__ out_sweeps) {
+  const int cell = blockIdx.x * kEigThreads + threadIdx.x;
+  const int scene = blockIdx.y;
+  if (cell >= cells) return;
+  partials += (size_t)scene * k_splits * kTerms * cells_padded;
+  tmats += (size_t)scene * 18;
   float *dst = out_h + ((size_t)scene * cells + cell) * 9;
+  int *sw = out_sweeps ? out_sweeps + (size_t)scene * cells + cell : nullptr;
+
+  double f[45];
+  {
+    double sum[kTerms];
+    combine_partials(partials, cells_padded, k_splits, cell, sum);
+    expand_gram(sum, f);
+  }
+  double trace = 0.0;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) dst[i] = (float)(o[i] * inv22);
-  if (out_sweeps) out_sweeps[(size_t)scene * cells + cell] = sweeps;
+  for (int i = 0; i < 9; ++i) trace += f[tri(i, i)];
+  double inv_d[9];
+  ldlt9(f, inv_d, trace * 1e-30 + 1e-300);
+  // fixed start vector with components of mixed size and sign (not orthogonal to anything special)
+  double h[9] = {0.31, -0.17, 0.43, 0.29, 0.37, -0.23, 0.41, 0.19, 0.47};
+  int iters = 0;
+  bool settled = false;
+  for (; iters < kMaxInvIter && !settled; ++iters) {
+    double y[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) y[i] = h[i];
+    ldlt9_solve(f, inv_d, y);
+    double nrm = 0.0, big = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      nrm = fma(y[i], y[i], nrm);
+      big = (fabs(y[i]) > fabs(big)) ? y[i] : big;
+    }
+    const double sc = copysign(rsqrt(nrm), big);       // unit norm, largest component positive
+    double diff = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double yi = y[i] * sc;
+      diff = fmax(diff, fabs(yi - h[i]));
+      h[i] = yi;
+    }
+    settled = diff <= 1e-10;                            // false for NaN
+  }
+  if (!settled || force_jacobi) {
+    eig_cell_jacobi(partials, tmats, cells_padded, k_splits, cell, dst, sw);
+    return;
+  }
+  denorm_store(h, tmats, dst);
+  if (sw) *sw = -iters;                                 // negative: inverse-iteration steps used
 }
 
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded, float *out_h,
-               int *out_sweeps, cudaStream_t st) {
+               int *out_sweeps, int force_jacobi, cudaStream_t st) {
   const GramPlan p = make_gram_plan(cells, n_kp_padded, sm_count_cached());
   dim3 grid((cells + kEigThreads - 1) / kEigThreads, batch);
   if (batch > 65535) return fail(APAP_E_TOOBIG, "eig: batch exceeds 65535");
-  k_eig<<<grid, kEigThreads, 0, st>>>(partials, tmats, cells, p.cells_padded, p.k_splits, out_h, out_sweeps);
+  k_eig<<<grid, kEigThreads, 0, st>>>(partials, tmats, cells, p.cells_padded, p.k_splits, force_jacobi, out_h,
+                                      out_sweeps);
   return check_cuda(cudaGetLastError(), "k_eig launch");
 }
 

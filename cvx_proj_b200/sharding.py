@@ -110,7 +110,6 @@ class ShardedAPAP:
         """Warp the owned canvas rows.  ``local_h_rows`` = this rank's rows of H (inverted in place,
         like ``APAP.local_warp``).  Returns a device tensor ``[n_px_rows, canvas_w, 3]``."""
         from . import _runtime as rt
-        from .apap import build_hinv_rows
 
         st, s = self.stitcher, self.me
         torch, device = rt.torch_cuda(st.device)
@@ -118,11 +117,10 @@ class ShardedAPAP:
         full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
         full[...] = np.eye(3, dtype=np.float32)
         full[s.cell_row0:s.cell_row1] = local_h_rows
-        rows = build_hinv_rows(full, self.col_cell, self.row_cell, int(st.offset_x), int(st.offset_y),
-                               int(ori_img.shape[1]), int(ori_img.shape[0]))
         src_dev = ori_img if not isinstance(ori_img, np.ndarray) else rt.to_device(torch, device, ori_img)
-        return st.warp_device(src_dev, rt.to_device(torch, device, rows), rt.to_device(torch, device, self.col_cell),
-                              rt.to_device(torch, device, self.row_cell), self.grid_cols, s.px_row0, s.px_row1)
+        tables = st.warp_tables_device(full, self.col_cell, self.row_cell, int(ori_img.shape[1]),
+                                       int(ori_img.shape[0]), device)
+        return st.warp_device(src_dev, tables, self.grid_cols, s.px_row0, s.px_row1)
 
     def panorama(self, band, group=None):
         return gather_bands(band, self.shards, int(self.stitcher.final_width), group)

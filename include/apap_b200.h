@@ -27,13 +27,13 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 1
+#define APAP_ABI_VERSION 2
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
-#define APAP_KP_ROW     28   /* floats per keypoint row: 24 product terms, kx, ky, 2 pad (112 B)  */
+#define APAP_KP_ROW     28   /* floats per keypoint row: 24 product terms, s*kx (x2), s*ky (x2)   */
 #define APAP_KP_CHUNK   128  /* keypoint rows per shared-memory stage; tables are padded to this  */
-#define APAP_HINV_ROW   12   /* floats per cell of the inverse grid: 9 H^-1, eps_x, eps_y, pad    */
+#define APAP_HINV_ROW   12   /* floats per cell of the warp's fast-path record (see apap_warp)    */
 
 #define APAP_E_BADARG   (-1)
 #define APAP_E_ALIGN    (-2)
@@ -57,31 +57,36 @@ int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
  * K1 -- weights + Gram contraction.  Replaces, for every cell, pyviz/apap.py:150-152 (the
  * weight w_i = max(exp(-|v - x_i| / sigma^2), gamma)) and the row scaling + SVD input build of
  * pyviz/apap.py:159: it accumulates S_t(cell) = sum_i w_i^2 * kp_table[i][t] for the 24 terms.
- *   kp_table : float [batch][n_kp_padded][APAP_KP_ROW]; rows past the real keypoints are zero
- *   anchors  : float [batch][cells][2]  (x, y) cell anchor points (get_vertice), float32
+ * Coordinates arrive pre-scaled by s = 2 log2(e) / sigma^2, so w_i^2 = max(2^-|s v - s x_i|, gamma^2).
+ *   kp_table : float [batch][n_kp_padded][APAP_KP_ROW]: 24 product terms, then s*kx, s*kx, s*ky,
+ *              s*ky (the keypoint, each coordinate twice); rows past the real keypoints are zero
+ *   anchors  : float [batch][cells][2] = s * (x, y) of the cell anchor points (get_vertice)
  *   partials : float [batch][k_splits][24][cells_padded]
- *   neg2_log2e_inv_sigma_sq = -2*log2(e)/sigma^2 ; gamma_sq = gamma^2
+ *   gamma_sq = gamma^2
  */
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells,
-                       int n_kp_padded, float neg2_log2e_inv_sigma_sq, float gamma_sq,
-                       float *partials, void *stream);
+                       int n_kp_padded, float gamma_sq, float *partials, void *stream);
 
 /*
  * K2 -- per-cell 9x9 symmetric eigensolve + de-normalisation.  Replaces cv.SVDecomp + V[-1]
  * (pyviz/apap.py:160-161) and pyviz/apap.py:164-168: sums the k_splits partials in float64,
- * expands the 24 sums to the 9x9 Gram matrix, runs cyclic Jacobi, takes the eigenvector of the
- * smallest eigenvalue h, and stores float32 H = T2inv * reshape(h,3,3) * T1, divided by H[2][2].
- *   tmats : double [batch][18] = T2inv (row-major 3x3) then T1, T2inv = inv(N2) inv(C2), T1 = C1 N1
- *   out_h : float [batch][cells][9]
- *   out_sweeps : optional int32 [batch][cells] Jacobi sweeps used (NULL to skip)
+ * expands the 24 sums to the 9x9 Gram matrix, finds the eigenvector h of its smallest eigenvalue
+ * and stores float32 H = T2inv * reshape(h,3,3) * T1, divided by H[2][2].
+ *   solver : APAP_EIG_AUTO = float64 LDL^T inverse iteration, cyclic Jacobi for the cells whose
+ *            iteration does not settle (tiny spectral gap); APAP_EIG_JACOBI = Jacobi for every cell
+ *   tmats  : double [batch][18] = T2inv (row-major 3x3) then T1, T2inv = inv(N2) inv(C2), T1 = C1 N1
+ *   out_h  : float [batch][cells][9]
+ *   out_sweeps : optional int32 [batch][cells]: > 0 Jacobi sweeps used, < 0 minus the number of
+ *            inverse-iteration steps (NULL to skip)
  */
+#define APAP_EIG_AUTO   0
+#define APAP_EIG_JACOBI 1
 int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells,
-                    int n_kp_padded, float *out_h, int *out_sweeps, void *stream);
+                    int n_kp_padded, int solver, float *out_h, int *out_sweeps, void *stream);
 
 /* K1 + K2 back to back on `stream` (what APAP.local_homography calls). */
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats,
-                          int batch, int cells, int n_kp_padded,
-                          float neg2_log2e_inv_sigma_sq, float gamma_sq,
+                          int batch, int cells, int n_kp_padded, float gamma_sq, int solver,
                           float *partials, float *out_h, int *out_sweeps, void *stream);
 
 /*
@@ -94,22 +99,25 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 
 /*
  * K3 -- mesh warp.  Replaces the pixel loop of APAP.local_warp (pyviz/apap.py:206-215): for the
- * canvas rows [row0, row1) looks the cell up (col_cell / row_cell tables = np.where(k < edges)
- * of :207,:209), applies that cell's H^-1 to (j - off_x, i - off_y, 1), divides, and copies
+ * canvas rows [row0, row1) looks the cell up (col_lut / row_lut = np.where(k < edges) of :207,:209),
+ * applies that cell's H^-1 to (j - off_x, i - off_y, 1), divides, and copies
  * src[int(ty)][int(tx)] when 0 < tx < src_w and 0 < ty < src_h (else leaves 0).  Pixel selection
- * is bit-identical to the reference's float64 arithmetic: a float32 fast path decides every pixel
- * whose coordinates are farther than the cell's guard band (eps_x, eps_y of the hinv row) from an
- * integer, the rest are recomputed in float64.
- *   hinv      : float [grid_rows*grid_cols][APAP_HINV_ROW]
- *   col_cell  : uint16 [canvas_w], row_cell : uint16 [canvas_h]
- *   out_band  : uint8 [(row1-row0)][canvas_w][3], 4-byte aligned; receives rows row0..row1-1
+ * is bit-identical to the reference's float64 arithmetic: a float32 fast path on cell-relative
+ * coefficients (cell_fast) decides every pixel whose coordinates are farther than the cell's
+ * guard band eps from an integer, the rest are recomputed in float64 from cell_hinv.
+ *   cell_fast : float [grid_rows*grid_cols][APAP_HINV_ROW] = A0 B0 C0 A1 B1 C1 A2 B2 C2,
+ *               int32 bits of (qbx - 0x4B400000), (qby - 0x4B400000), eps; with dx, dy the pixel's
+ *               offset inside its cell:  src_x = qbx + floor((A0 dx + B0 dy + C0) / (A2 dx + B2 dy + C2))
+ *   cell_hinv : float [grid_rows*grid_cols][9], the inverted grid of pyviz/apap.py:201-203
+ *   col_lut   : uint32 [canvas_w] = cell column | dx << 16;  row_lut : uint32 [canvas_h] likewise
+ *   out_band  : uint8 [(row1-row0)][canvas_w][3], 8-byte aligned; receives rows row0..row1-1
  *   centre    : optional uint8 [centre_h][centre_w][3] pasted at (off_x, off_y) and blended with
  *               the warped pixel by the uniform_blend rule (fused K3+K4, pyviz/apap.py:259-261);
  *               NULL = plain warp
  *   force_exact : non-zero = every pixel takes the float64 path (validation switch)
  */
-int apap_warp(const uint8_t *src, int src_h, int src_w, const float *hinv,
-              const uint16_t *col_cell, const uint16_t *row_cell, int grid_cols,
+int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
+              const uint32_t *col_lut, const uint32_t *row_lut, int grid_cols,
               int canvas_w, int canvas_h, int off_x, int off_y, int row0, int row1,
               const uint8_t *centre, int centre_h, int centre_w,
               uint8_t *out_band, int force_exact, void *stream);

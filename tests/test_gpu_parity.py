@@ -135,6 +135,50 @@ def test_cell_row_sharding_is_bitwise_identical():
         assert np.array_equal(part, full[r0:r1])
 
 
+def test_eig_solvers_agree_and_report():
+    """AUTO (float64 LDL^T inverse iteration) and JACOBI (full FP32 diagonalisation) give the same
+    grid; out_sweeps tells which one ran per cell."""
+    import torch
+    from cvx_proj_b200.apap import scale_anchors, weight_scale
+    sc = synth.make_scene("c1", mesh=40)
+    st = _stitcher(sc)
+    table, tmats = st._prepare(sc.src, sc.dst)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = torch.from_numpy(table[None]).to(dev)
+    a = torch.from_numpy(scale_anchors(sc.vertices, weight_scale(sc.sigma))[None]).to(dev)
+    m = torch.from_numpy(tmats[None]).to(dev)
+    cells = 40 * 40
+    out = {}
+    for solver in (rt.EIG_AUTO, rt.EIG_JACOBI):
+        sw = torch.zeros((1, cells), dtype=torch.int32, device=dev)
+        h = st.local_homography_device(t, a, m, 1, cells, sweeps=sw, solver=solver)
+        out[solver] = (h.cpu().numpy().reshape(40, 40, 3, 3), sw.cpu().numpy().ravel())
+    h_auto, sw_auto = out[rt.EIG_AUTO]
+    h_jac, sw_jac = out[rt.EIG_JACOBI]
+    assert (sw_auto < 0).all() and (sw_auto >= -6).all(), (sw_auto.min(), sw_auto.max())
+    assert (sw_jac > 0).all() and (sw_jac <= 12).all()
+    assert _herr(h_auto, h_jac, sc).max() <= 2e-5
+    ref = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+    print(f"eig: auto vs gram64 {_herr(h_auto, ref, sc).max():.2e}, jacobi vs gram64 {_herr(h_jac, ref, sc).max():.2e}, "
+          f"inverse-iteration steps {-sw_auto.max()}..{-sw_auto.min()}, jacobi sweeps {sw_jac.min()}..{sw_jac.max()}")
+    assert _herr(h_auto, ref, sc).max() <= H_GATE and _herr(h_jac, ref, sc).max() <= H_GATE
+
+
+def test_degenerate_keypoints_fall_back_to_jacobi():
+    """Collinear keypoints: the Gram matrix has a multi-dimensional null space, inverse iteration
+    cannot settle on a direction-independent answer -> those cells take the Jacobi path (or settle
+    on a null vector); the result must be finite either way, as it is for the reference's SVD."""
+    import torch
+    sc = synth.make_scene("mini", mesh=6)
+    src = sc.src.copy()
+    src[:, 1] = 0.5 * src[:, 0] + 3.0
+    dst = src + np.float32(2.0)
+    h, _ = _stitcher(sc).local_homography(src, dst, sc.vertices)
+    assert h.shape == (6, 6, 3, 3)
+    assert np.isfinite(h[..., 2, 2]).all()
+    torch.cuda.synchronize()
+
+
 # --------------------------------------------------------------------------------- mesh warp
 @pytest.mark.parametrize("name", ["tiny", "mini"])
 def test_local_warp_bit_exact_vs_reference_golden(golden, name):
