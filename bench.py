@@ -249,11 +249,12 @@ class Pass:
         inv = np.linalg.inv(h).astype(np.float32)
         img = sc.image(1)
         centre = synth.make_image(sc.width, sc.height, seed=2)
-        self.tables = self.st.warp_tables_device(inv, self.col_cell, self.row_cell, sc.width, sc.height, self.device)
+        self.px_rows = px_rows if px_rows is not None else (0, sc.final_h)
+        self.tables = self.st.warp_tables_device(inv, self.col_cell, self.row_cell, sc.width, sc.height, self.device,
+                                                 self.px_rows[0], self.px_rows[1])
         self.flagged_cells = self.tables.exact_cells_frac
         self.img = torch.from_numpy(img).to(self.device)
         self.centre = torch.from_numpy(centre).to(self.device)
-        self.px_rows = px_rows if px_rows is not None else (0, sc.final_h)
         n = self.px_rows[1] - self.px_rows[0]
         self.canvas = torch.empty((n, sc.final_w, 3), dtype=torch.uint8, device=self.device)
         self.canvas2 = torch.empty_like(self.canvas)
@@ -261,7 +262,7 @@ class Pass:
         self.host_img, self.host_centre = img, centre
 
     def warp(self, fused=False):
-        self.st.warp_device(self.img, self.tables, self.sc.mesh_cells, self.px_rows[0], self.px_rows[1], centre_dev=self.centre if fused else None,
+        self.st.warp_device(self.img, self.tables, self.sc.mesh_cells, centre_dev=self.centre if fused else None,
                             out=self.canvas)
 
     def blend(self):

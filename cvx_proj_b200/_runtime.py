@@ -17,6 +17,7 @@ GRAM_TERMS = 24
 KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
+WARP_GROUP_ROWS = 8
 ABI_VERSION = 2
 EIG_AUTO = 0
 EIG_JACOBI = 1
@@ -32,8 +33,8 @@ SIGNATURES = {
     "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "apap_local_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
-    "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                          c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                          c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "apap_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "apap_fp32_probe": (c_int, [c_int, c_void_p, POINTER(c_double), c_void_p]),
 }

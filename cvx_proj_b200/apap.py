@@ -25,9 +25,9 @@ from typing import NamedTuple
 import numpy as np
 
 from . import _runtime as rt
-from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW
+from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW, WARP_GROUP_ROWS
 
-__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "cell_lookup_tables"]
+__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "build_row_groups", "cell_lookup_tables"]
 
 _U = 2.0 ** -24          # float32 unit roundoff
 
@@ -129,10 +129,11 @@ def _cell_extent(lut: np.ndarray, n: int):
 
 def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndarray, off_x: int, off_y: int,
                       src_w: int, src_h: int):
-    """Kernel inputs of the mesh warp: ``(cell_fast[cells, 12] f32, col_lut[W, 2] u32, row_lut[H, 2] u32)``.
+    """Kernel inputs of the mesh warp: ``(cell_fast[cells, 12] f32, col_lut[W, 2] u32, row_first[grid_rows] i64)``.
 
     ``col_lut[j] = (cell column, float32 bits of dx)`` with ``dx = j - (first canvas column of that
-    cell)``; ``row_lut`` likewise.  ``cell_fast`` holds, per cell, the float32 fast path of
+    cell)``; ``row_first[m]`` is the first canvas row of cell row m (``dy = i - row_first``, see
+    ``build_row_groups``).  ``cell_fast`` holds, per cell, the float32 fast path of
     ``csrc/warp_blend.cu``: with ``(x0, y0)`` the cell's first pixel minus the canvas offsets, the
     reference's ``t = H^-1 [x0 + dx, y0 + dy, 1]`` (pyviz/apap.py:211-213) is rewritten as
 
@@ -145,7 +146,9 @@ def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndar
     numerator, ``rcp.approx`` and one multiply); a quotient farther than eps from every integer
     gets the same floor and bounds decision as the reference's float64, the kernel recomputes the
     others in float64.  ``0.5 - eps = -1`` sends the whole cell to the float64 path (denominator
-    changes sign or varies too much inside the cell, coordinates beyond 2^20, non-finite entries).
+    changes sign or varies too much inside the cell, coordinates beyond 2^20, non-finite entries);
+    ``2`` marks a cell whose four corner pixels, and therefore all its pixels, map outside the
+    source image by more than half a pixel: the kernel leaves it black without any arithmetic.
     """
     gr, gc = inv_h.shape[0], inv_h.shape[1]
     h = inv_h.astype(np.float64).reshape(gr, gc, 9)
@@ -159,9 +162,6 @@ def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndar
     col_lut = np.empty((col_cell.shape[0], 2), dtype=np.uint32)
     col_lut[:, 0] = col_cell
     col_lut[:, 1] = (np.arange(col_cell.shape[0]) - jlo[col64]).astype(np.float32).view(np.uint32)
-    row_lut = np.empty((row_cell.shape[0], 2), dtype=np.uint32)
-    row_lut[:, 0] = row_cell
-    row_lut[:, 1] = (np.arange(row_cell.shape[0]) - ilo[row64]).astype(np.float32).view(np.uint32)
 
     x0 = (jlo - off_x).astype(np.float64)[None, :]
     y0 = (ilo - off_y).astype(np.float64)[:, None]
@@ -202,6 +202,14 @@ def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndar
             eps = np.maximum(eps, np.where(np.isfinite(e), e, 1.0))
         eps = 1.25 * eps + 1e-7
         ok &= eps < 0.25
+        # cells that map entirely outside the source image: tx - c and ty - c are ratios of functions affine
+        # in (dx, dy) with a positive denominator, so their sign over the rectangle is decided at its corners
+        cx = np.stack([cxx for cxx in (0.0 * dxm, dxm) for _ in (0, 1)], axis=-1) + 0.0 * dym[..., None]
+        cy = np.stack([cyy for _ in (0, 1) for cyy in (0.0 * dym, dym)], axis=-1) + 0.0 * dxm[..., None]
+        dc = np.where(ok[..., None], corners, 1.0)
+        qx = (coef[..., 0:1] * cx + coef[..., 1:2] * cy + coef[..., 2:3]) / dc + bx[..., None]
+        qy = (coef[..., 3:4] * cx + coef[..., 4:5] * cy + coef[..., 5:6]) / dc + by[..., None]
+        outside = ok & ((qx < -0.5).all(-1) | (qx > src_w + 0.5).all(-1) | (qy < -0.5).all(-1) | (qy > src_h + 0.5).all(-1))
     rec = np.zeros((gr, gc, HINV_ROW), dtype=np.float32)
     rec[..., 0:9] = np.where(ok[..., None], coef, 0.0)
     rec[..., 8] = np.where(ok, rec[..., 8], 1.0)
@@ -211,8 +219,35 @@ def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndar
     hme = np.where(ok, 0.5 - eps, -1.0)
     hme32 = hme.astype(np.float32)
     hme32 = np.where(hme32.astype(np.float64) > hme, np.nextafter(hme32, np.float32(-2)), hme32)   # round down
-    rec[..., 11] = hme32
-    return rec.reshape(gr * gc, HINV_ROW), col_lut, row_lut
+    rec[..., 11] = np.where(outside, np.float32(2.0), hme32)          # 2 = "every pixel of the cell is left black"
+    return rec.reshape(gr * gc, HINV_ROW), col_lut, ilo
+
+
+def build_row_groups(row_cell: np.ndarray, row_first: np.ndarray, row0: int = 0, row1=None,
+                     max_rows: int = WARP_GROUP_ROWS) -> np.ndarray:
+    """Work list of the mesh warp for the canvas rows ``[row0, row1)``: ``uint32 [n_groups, 4]`` =
+    ``(first canvas row, rows in the group, cell row, float32 bits of dy of the first row)``.
+
+    Every maximal run of canvas rows with the same cell row (``row_cell``, pyviz/apap.py:207) is cut
+    into ``ceil(len / max_rows)`` groups of near-equal height, so a group never crosses a cell row
+    and a lane of the kernel needs one cell record for all its pixels."""
+    row1 = row_cell.shape[0] if row1 is None else row1
+    rc = row_cell[row0:row1].astype(np.int64)
+    if rc.size == 0:
+        return np.zeros((0, 4), dtype=np.uint32)
+    starts = np.flatnonzero(np.r_[True, rc[1:] != rc[:-1]])
+    lens = np.diff(np.r_[starts, rc.size])
+    parts = -(-lens // max_rows)                                  # groups per run
+    run = np.repeat(np.arange(starts.size), parts)                 # run index of every group
+    k = np.arange(run.size) - np.repeat(np.cumsum(parts) - parts, parts)     # group index inside its run
+    lo = starts[run] + (k * lens[run]) // parts[run]
+    hi = starts[run] + ((k + 1) * lens[run]) // parts[run]
+    groups = np.empty((run.size, 4), dtype=np.uint32)
+    groups[:, 0] = lo + row0
+    groups[:, 1] = hi - lo
+    groups[:, 2] = rc[lo]
+    groups[:, 3] = (lo + row0 - row_first[rc[lo]]).astype(np.float32).view(np.uint32)
+    return groups
 
 
 class _PinnedStage:
@@ -245,11 +280,15 @@ class _PinnedStage:
 
 
 class WarpTables(NamedTuple):
-    """Device-resident inputs of ``apap_warp`` for one inverted grid (see ``build_warp_tables``)."""
+    """Device-resident inputs of ``apap_warp`` for one inverted grid and one band of canvas rows
+    (see ``build_warp_tables`` / ``build_row_groups``)."""
     cell_fast: object       # float32 [cells * 12]
     cell_hinv: object       # float32 [cells * 9]
     col_lut: object         # int32 [canvas_w * 2]
-    row_lut: object         # int32 [canvas_h * 2]
+    row_groups: object      # int32 [n_groups * 4]
+    n_groups: int
+    row0: int               # the band of canvas rows the groups cover
+    row1: int
     exact_cells_frac: float  # share of cells whose every pixel takes the float64 path
 
 
@@ -495,38 +534,38 @@ class APAP:
             self._lut_cache = {key: hit}
         return hit
 
-    def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None):
-        """Build the warp kernel's tables (``build_warp_tables``) for an inverted grid and upload them
-        with one host->device copy.  Returns ``WarpTables`` (device tensors)."""
+    def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None, row0=0, row1=None):
+        """Build the warp kernel's tables (``build_warp_tables`` + ``build_row_groups`` for the canvas
+        rows ``[row0, row1)``) for an inverted grid and upload them with one host->device copy."""
         torch, device = rt.torch_cuda(device if device is not None else self.device)
-        fast, col_lut, row_lut = build_warp_tables(inv_h, col_cell, row_cell, int(self.offset_x), int(self.offset_y),
-                                                   int(src_w), int(src_h))
+        row1 = int(self.final_height) if row1 is None else row1
+        fast, col_lut, row_first = build_warp_tables(inv_h, col_cell, row_cell, int(self.offset_x),
+                                                     int(self.offset_y), int(src_w), int(src_h))
+        groups = build_row_groups(row_cell, row_first, row0, row1)
         hinv = np.ascontiguousarray(inv_h, dtype=np.float32).reshape(-1, 9)
         if not hasattr(self, "_warp_stage"):
             self._warp_stage = _PinnedStage()
-        views = self._warp_stage.upload(torch, device, (fast, hinv, col_lut, row_lut))
+        views = self._warp_stage.upload(torch, device, (fast, hinv, col_lut, groups))
         return WarpTables(views[0].view(torch.float32), views[1].view(torch.float32),
-                          views[2].view(torch.int32), views[3].view(torch.int32),
-                          float((fast[:, 11] < 0).mean()))
+                          views[2].view(torch.int32), views[3].view(torch.int32), int(groups.shape[0]),
+                          int(row0), int(row1), float((fast[:, 11] < 0).mean()))
 
-    def warp_device(self, src_dev, tables, grid_cols, row0=0, row1=None, centre_dev=None, out=None,
-                    force_exact=False):
-        """Device-resident K3 (optionally fused with K4): writes canvas rows ``[row0, row1)`` into
-        ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None)."""
+    def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False):
+        """Device-resident K3 (optionally fused with K4): writes the canvas rows ``[tables.row0,
+        tables.row1)`` into ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None)."""
         torch, device = rt.torch_cuda(src_dev.device)
         lib = rt.load_library()
-        fw, fh = int(self.final_width), int(self.final_height)
-        row1 = fh if row1 is None else row1
+        fw = int(self.final_width)
         if out is None:
-            out = torch.empty((row1 - row0, fw, 3), dtype=torch.uint8, device=device)
+            out = torch.empty((tables.row1 - tables.row0, fw, 3), dtype=torch.uint8, device=device)
         ch, cw = (centre_dev.shape[0], centre_dev.shape[1]) if centre_dev is not None else (0, 0)
         with torch.cuda.device(device):
             rt.check(lib.apap_warp(
                 src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
-                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_lut.data_ptr(), grid_cols, fw, fh,
-                int(self.offset_x), int(self.offset_y), row0, row1,
+                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_groups.data_ptr(),
+                tables.n_groups, grid_cols, fw, int(self.offset_x), int(self.offset_y), tables.row0,
                 centre_dev.data_ptr() if centre_dev is not None else None, ch, cw, out.data_ptr(),
-                1 if force_exact else 0, rt.stream_ptr(torch, device)), "apap_warp")
+                out.numel(), int(force_exact), rt.stream_ptr(torch, device)), "apap_warp")
         return out
 
     def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False):

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ p
       nrm = fma(y[i], y[i], nrm);
       big = (fabs(y[i]) > fabs(big)) ? y[i] : big;
     }
+    if (!(nrm > 0.0 && nrm < 1e300)) break;            // overflow / NaN (rank-deficient matrix): not settled
     const double sc = copysign(rsqrt(nrm), big);       // unit norm, largest component positive
     double diff = 0.0;
 #pragma unroll
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ p
       diff = fmax(diff, fabs(yi - h[i]));
       h[i] = yi;
     }
-    settled = diff <= 1e-10;                            // false for NaN
+    settled = diff <= 1e-10;
   }
   if (!settled || force_jacobi) {
     eig_cell_jacobi(partials, tmats, cells_padded, k_splits, cell, dst, sw);

@@ -2,12 +2,16 @@
 // fused with K4, and K4 -- uniform_blend (pyviz/apap_utils.py:75-88).
 //
 // HBM-bound byte work: every canvas pixel is written once (3 B), every source pixel is read at
-// most once from HBM.  Thread layout: a warp owns 32 consecutive canvas columns x P consecutive
-// rows; lane l works on column j0 + l, so in every row the 32 lanes gather ~96 contiguous source
-// bytes (1-2 L1 wavefronts per byte plane instead of one line per lane) and their 32 pixels are
-// 96 contiguous output bytes, which the warp re-packs with two shuffles + one byte-permute into
-// 24 aligned 32-bit stores.  A thread keeps its cell column (and the cell record) across its P
-// rows and reloads only when the cell row changes.
+// most once from HBM.  Work unit: a warp owns 32 consecutive canvas columns x one "row group" =
+// up to 8 consecutive canvas rows of ONE cell row (the host cuts every cell row into such
+// groups), so a lane (= one column) needs exactly one cell record for all its pixels and the
+// whole index computation is straight-line code.  In every row the 32 lanes gather ~96
+// contiguous source bytes (1-2 L1 wavefronts per byte plane instead of one line per lane) and
+// their 32 pixels are 96 contiguous output bytes, which the warp re-packs with two shuffles +
+// one byte-permute into 24 aligned 32-bit stores.  Three phases per warp so that all of a
+// lane's gathers are in flight together: (1) source index of every row on packed FP32x2
+// arithmetic, two rows per instruction, (2) issue every byte load, (3) combine, blend,
+// re-pack, store.
 //
 // Pixel selection must equal the reference's float64 arithmetic (float32 H^-1 promoted to
 // float64, divide, strict bounds, truncate).  The float32 fast path works in cell-relative
@@ -17,33 +21,34 @@
 // float32 error is ~1e-5 px:   src_x = qbx + floor((A0 dx + B0 dy + C0) / (A2 dx + B2 dy + C2)).
 // The host also supplies, per cell, a rigorous bound eps on that error.  A quotient farther than
 // eps from every integer has the same floor and the same bounds decision in both arithmetics;
-// the others (~1e-4 of the pixels) are recomputed in float64 exactly as the reference does.
+// the others (~1e-4 of the pixels) are flagged and recomputed in float64 exactly as the
+// reference does, after the straight-line part.
 #include "common.cuh"
 
 namespace apap {
 
 constexpr int kWarpThreads = 256;
 constexpr int kWarpsPerCta = kWarpThreads / 32;
-constexpr int kRowsPerThread = 8;
+constexpr int kRowsPerGroup = APAP_WARP_GROUP_ROWS;   // even: rows are processed in pairs
+static_assert(kRowsPerGroup % 2 == 0, "rows are processed in pairs");
 
 struct WarpParams {
   const uint8_t *src;
-  const float4 *cell_fast;     // [cells][3] float4: A0 B0 C0 A1 | B1 C1 A2 B2 | C2 qbx' qby' (int bits) 0.5-eps
+  const float4 *cell_fast;     // [cells][3] float4: A0 B0 C0 A1 | B1 C1 A2 B2 | C2 qbx' qby' (int bits) g
   const float *cell_hinv;      // [cells][9]: the reference's inverted grid (float64 path only)
   const uint2 *col_lut;        // [canvas_w]: {cell column, float bits of x - cell's first x}
-  const uint2 *row_lut;        // [canvas_h]: {cell row,    float bits of y - cell's first y}
+  const uint4 *row_groups;     // [n_groups]: {first canvas row, rows (1..8), cell row, float bits of dy of the first row}
   const uint8_t *centre;
   uint8_t *out;                // first byte of canvas row `row0`
-  int row0, row1;              // band of canvas rows
+  int row0;                    // first canvas row of the band `out` holds
   int chunks_per_row;          // ceil(canvas_w / 32)
-  int n_warps;                 // chunks_per_row * ceil((row1 - row0) / P)
+  int n_warps;                 // chunks_per_row * n_groups
   int src_h, src_w;
   int grid_cols;
   int canvas_w;
   int off_x, off_y;
   int centre_h, centre_w;
   int force_exact;
-  int word_stores;             // canvas_w % 4 == 0 and out 4-byte aligned: packed 32-bit stores
 };
 
 constexpr float kMagic = 12582912.f;          // 1.5 * 2^23: x + kMagic (round down) = floor(x) in the mantissa
@@ -61,112 +66,132 @@ __device__ __noinline__ int exact_lookup(const float *__restrict__ h, int x, int
   return -1;
 }
 
-__device__ __forceinline__ uint32_t load_px(const uint8_t *__restrict__ p) {
-  const uint32_t b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2);
-  return __byte_perm(__byte_perm(b0, b1, 0x1140), b2, 0x3410);     // zero-extended bytes -> b0 | b1<<8 | b2<<16
-}
-
-// One canvas row of one lane.  kWords: the band's rows are 4-byte aligned (canvas_w % 4 == 0), the
-// warp's 32 pixels leave as 24 packed 32-bit stores; otherwise three byte stores per lane.
-template <bool kBlend, bool kWords>
-__device__ __forceinline__ void warp_row(const WarpParams &p, const uint8_t *__restrict__ src, int i, int x, bool col_ok,
-                                         const uint2 cl, int &cur_row_cell, int &cell, float dxf, float &b0,
-                                         float &b1, float &b2, float &m0, float &m1, float &m2, float &hme,
-                                         int &qbx, int &qby, int lane_a, int lane_b, uint32_t sel, bool store_ok,
-                                         uint8_t *dst) {
-  const uint2 rl = __ldg(p.row_lut + i);           // same address in every lane
-  if ((int)rl.x != cur_row_cell) {                 // warp-uniform: new cell row -> new record
-    cur_row_cell = (int)rl.x;
-    cell = cur_row_cell * p.grid_cols + (int)cl.x;
-    const float4 *rec = p.cell_fast + (size_t)cell * 3;
-    const float4 u = __ldg(rec), v = __ldg(rec + 1), w = __ldg(rec + 2);
-    m0 = fmaf(u.x, dxf, u.z); b0 = u.y;
-    m1 = fmaf(u.w, dxf, v.y); b1 = v.x;
-    m2 = fmaf(v.z, dxf, w.x); b2 = v.w;
-    qbx = __float_as_int(w.y);
-    qby = __float_as_int(w.z);
-    hme = p.force_exact ? -1.f : w.w;
-  }
-  const float dyf = __uint_as_float(rl.y);
-  const float n0 = fmaf(b0, dyf, m0);
-  const float n1 = fmaf(b1, dyf, m1);
-  const float d = fmaf(b2, dyf, m2);
-  const float r = rcp_approx(d);
-  const float qx = n0 * r;
-  const float qy = n1 * r;
-  const float tx = add_rd(qx, kMagic);
-  const float ty = add_rd(qy, kMagic);
-  const float fx = qx - (tx - kMagic);             // exact fractional parts in [0, 1)
-  const float fy = qy - (ty - kMagic);
-  // hme = 0.5 - eps; a record with hme < 0 (degenerate cell, forced) never passes; NaN never passes
-  const bool clear = fmaxf(fabsf(fx - 0.5f), fabsf(fy - 0.5f)) <= hme;
-  const int ix = __float_as_int(tx) + qbx;         // qbx already holds (base - bits(kMagic))
-  const int iy = __float_as_int(ty) + qby;
-  bool inb = ((unsigned)ix < (unsigned)p.src_w) & ((unsigned)iy < (unsigned)p.src_h);
-  int idx = iy * p.src_w + ix;
-  if (!clear) {
-    idx = exact_lookup(p.cell_hinv + (size_t)cell * 9, x, i - p.off_y, p.src_w, p.src_h);
-    inb = idx >= 0;
-  }
-  uint32_t val = 0;
-  if (inb) val = load_px(src + (size_t)(unsigned)idx * 3);
-  if (kBlend) {
-    // centre image pasted at (off_x, off_y) (pyviz/apap.py:259-260), then uniform_blend
-    const int cy = i - p.off_y;
-    if ((unsigned)cy < (unsigned)p.centre_h && (unsigned)x < (unsigned)p.centre_w && col_ok) {
-      const uint32_t cv = load_px(p.centre + ((size_t)cy * p.centre_w + x) * 3);
-      if (cv != 0) val = (val != 0) ? __vhaddu4(val, cv) : cv;
-    }
-  }
-  if (kWords) {
-    const uint32_t va = __shfl_sync(0xffffffffu, val, lane_a);
-    const uint32_t vb = __shfl_sync(0xffffffffu, val, lane_b);
-    if (store_ok) *reinterpret_cast<uint32_t *>(dst) = __byte_perm(va, vb, sel);
-  } else if (store_ok) {
-    dst[0] = (uint8_t)val;
-    dst[1] = (uint8_t)(val >> 8);
-    dst[2] = (uint8_t)(val >> 16);
-  }
-}
-
+// kWords: the band's rows are 4-byte aligned (canvas_w % 4 == 0): the warp's 32 pixels of a row
+// leave as 24 packed 32-bit stores; otherwise three byte stores per lane.
 template <bool kBlend, bool kWords>
 __global__ void __launch_bounds__(kWarpThreads) k_warp(const WarpParams p) {
-  constexpr int P = kRowsPerThread;
+  constexpr int P = kRowsPerGroup;
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (wid >= p.n_warps) return;                    // warp-uniform
-  const int rg = wid / p.chunks_per_row;
-  const int j0 = (wid - rg * p.chunks_per_row) * 32;
-  const int i0 = p.row0 + rg * P;
-  const int n_rows = min(P, p.row1 - i0);
+  const int g = wid / p.chunks_per_row;
+  const int j0 = (wid - g * p.chunks_per_row) * 32;
+  const uint4 grp = __ldg(p.row_groups + g);       // same address in every lane
+  const int i0 = (int)grp.x, n_rows = (int)grp.y;
   const int j = j0 + lane;
   const bool col_ok = j < p.canvas_w;
   const uint2 cl = __ldg(p.col_lut + (col_ok ? j : p.canvas_w - 1));
-  const float dxf = __uint_as_float(cl.y);
-  const int x = j - p.off_x;
-  const uint8_t *__restrict__ src = p.src;
+  const int cell = (int)grp.z * p.grid_cols + (int)cl.x;
+  const float4 *rec = p.cell_fast + (size_t)cell * 3;
+  const float4 u = __ldg(rec), v = __ldg(rec + 1), w = __ldg(rec + 2);
+  const int x = j - p.off_x, y0 = i0 - p.off_y;
 
-  // store side.  kWords: output word w = lane (< 24) takes its 4 bytes from the pixels of lanes
-  // lane_a = (4w)/3 and lane_a + 1, starting at byte (4w) % 3 of the first
+  // ---- phase 1: source pixel index of every row (-1 = leave black) ---------------------------
+  int idx[P];
+  const bool outside = w.w > 1.f && !p.force_exact;          // the whole cell maps outside the source
+  if (__all_sync(0xffffffffu, outside)) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) idx[k] = -1;
+  } else {
+    const float dxf = __uint_as_float(cl.y), dy0 = __uint_as_float(grp.w);
+    const float m0 = fmaf(u.x, dxf, u.z), m1 = fmaf(u.w, dxf, v.y), m2 = fmaf(v.z, dxf, w.x);
+    const float b0 = u.y, b1 = v.x, b2 = v.w;
+    const int qbx = __float_as_int(w.y), qby = __float_as_int(w.z);   // integer base - bits(kMagic)
+    // g = 0.5 - eps; a record with g < 0 (degenerate cell, forced) never passes; NaN never passes
+    const float hme = p.force_exact ? -1.f : w.w;
+    const float2 km = make_float2(kMagic, kMagic), nkm = make_float2(-kMagic, -kMagic), nh = make_float2(-0.5f, -0.5f);
+    unsigned flagged = 0;                           // rows whose quotient is inside the guard band
+#pragma unroll
+    for (int k = 0; k < P; k += 2) {
+      // two rows at once on packed FP32x2 arithmetic (identical roundings to the scalar form)
+      const float2 dy = make_float2(dy0 + (float)k, dy0 + (float)(k + 1));
+      const float2 n0 = __ffma2_rn(make_float2(b0, b0), dy, make_float2(m0, m0));
+      const float2 n1 = __ffma2_rn(make_float2(b1, b1), dy, make_float2(m1, m1));
+      const float2 d = __ffma2_rn(make_float2(b2, b2), dy, make_float2(m2, m2));
+      const float2 r = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+      const float2 qx = __fmul2_rn(n0, r), qy = __fmul2_rn(n1, r);
+      const float2 tx = __fadd2_rd(qx, km), ty = __fadd2_rd(qy, km);             // floor + kMagic
+      const float2 gx = __fadd2_rn(tx, nkm), gy = __fadd2_rn(ty, nkm);           // floor
+      const float2 fx = __fadd2_rn(qx, make_float2(-gx.x, -gx.y));               // exact fraction in [0, 1)
+      const float2 fy = __fadd2_rn(qy, make_float2(-gy.x, -gy.y));
+      const float2 hx = __fadd2_rn(fx, nh), hy = __fadd2_rn(fy, nh);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float txe = e ? tx.y : tx.x, tye = e ? ty.y : ty.x;
+        const float hxe = e ? hx.y : hx.x, hye = e ? hy.y : hy.x;
+        const bool clear = fmaxf(fabsf(hxe), fabsf(hye)) <= hme;
+        const int ix = __float_as_int(txe) + qbx;
+        const int iy = __float_as_int(tye) + qby;
+        const bool inb = ((unsigned)ix < (unsigned)p.src_w) & ((unsigned)iy < (unsigned)p.src_h);
+        idx[k + e] = (inb && !outside) ? iy * p.src_w + ix : -1;
+        if (!clear && !outside) flagged |= 1u << (k + e);
+      }
+    }
+    flagged &= (1u << n_rows) - 1u;
+    if (__any_sync(0xffffffffu, flagged != 0)) {    // rare: re-decide the flagged pixels in float64
+      const float *h = p.cell_hinv + (size_t)cell * 9;
+#pragma unroll
+      for (int k = 0; k < P; ++k)
+        if (flagged & (1u << k)) idx[k] = exact_lookup(h, x, y0 + k, p.src_w, p.src_h);
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if (k >= n_rows) idx[k] = -1;
+  }
+
+  // ---- phase 2: every byte load of the lane in flight together --------------------------------
+  const uint8_t *__restrict__ src = p.src;
+  uint32_t b0[P], b1[P], b2[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    b0[k] = b1[k] = b2[k] = 0;
+    if (idx[k] >= 0) {
+      const uint8_t *q = src + (size_t)(unsigned)idx[k] * 3;
+      b0[k] = __ldg(q); b1[k] = __ldg(q + 1); b2[k] = __ldg(q + 2);
+    }
+  }
+  uint32_t c0[kBlend ? P : 1], c1[kBlend ? P : 1], c2[kBlend ? P : 1];
+  if (kBlend) {
+    // centre image pasted at (off_x, off_y) (pyviz/apap.py:259-260)
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int cy = y0 + k;
+      c0[k] = c1[k] = c2[k] = 0;
+      if (k < n_rows && (unsigned)cy < (unsigned)p.centre_h && (unsigned)x < (unsigned)p.centre_w && col_ok) {
+        const uint8_t *q = p.centre + ((size_t)cy * p.centre_w + x) * 3;
+        c0[k] = __ldg(q); c1[k] = __ldg(q + 1); c2[k] = __ldg(q + 2);
+      }
+    }
+  }
+
+  // ---- phase 3: combine, blend, re-pack across the warp, store --------------------------------
+  // kWords: output word w = lane (< 24) takes its 4 bytes from the pixels of lanes lane_a = (4w)/3
+  // and lane_a + 1, starting at byte (4w) % 3 of the first
   const int lane_a = (lane + lane / 3) & 31, lane_b = (lane_a + 1) & 31;
   const uint32_t sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
   const bool store_ok = kWords ? lane < min(24, (3 * (p.canvas_w - j0)) >> 2) : col_ok;
-  const size_t pitch = (size_t)p.canvas_w * 3;
-  uint8_t *dst = p.out + ((size_t)(i0 - p.row0) * p.canvas_w + j0) * 3 + (kWords ? 4 : 3) * lane;
-
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 1.f, hme = -1.f;
-  int qbx = 0, qby = 0;
-  int cur_row_cell = -1, cell = 0;
-
-  if (n_rows == P) {
+  const uint32_t pitch = (uint32_t)p.canvas_w * 3u;                 // the band is < 2^31 bytes (launch_warp)
+  uint32_t off = ((uint32_t)(i0 - p.row0) * (uint32_t)p.canvas_w + (uint32_t)j0) * 3u + (kWords ? 4u : 3u) * lane;
 #pragma unroll
-    for (int k = 0; k < P; ++k)
-      warp_row<kBlend, kWords>(p, src, i0 + k, x, col_ok, cl, cur_row_cell, cell, dxf, b0, b1, b2, m0, m1, m2, hme,
-                               qbx, qby, lane_a, lane_b, sel, store_ok, dst + k * pitch);
-  } else {
-    for (int k = 0; k < n_rows; ++k)
-      warp_row<kBlend, kWords>(p, src, i0 + k, x, col_ok, cl, cur_row_cell, cell, dxf, b0, b1, b2, m0, m1, m2, hme,
-                               qbx, qby, lane_a, lane_b, sel, store_ok, dst + k * pitch);
+  for (int k = 0; k < P; ++k) {
+    if (k < n_rows) {                              // warp-uniform
+      uint32_t val = __byte_perm(__byte_perm(b0[k], b1[k], 0x1140), b2[k], 0x3410);   // b0 | b1<<8 | b2<<16
+      if (kBlend) {                                // uniform_blend (pyviz/apap_utils.py:75-88)
+        const uint32_t cv = __byte_perm(__byte_perm(c0[k], c1[k], 0x1140), c2[k], 0x3410);
+        if (cv != 0) val = (val != 0) ? __vhaddu4(val, cv) : cv;
+      }
+      uint8_t *d = p.out + off;
+      if (kWords) {
+        const uint32_t va = __shfl_sync(0xffffffffu, val, lane_a);
+        const uint32_t vb = __shfl_sync(0xffffffffu, val, lane_b);
+        if (store_ok) *reinterpret_cast<uint32_t *>(d) = __byte_perm(va, vb, sel);
+      } else if (store_ok) {
+        d[0] = (uint8_t)val;
+        d[1] = (uint8_t)(val >> 8);
+        d[2] = (uint8_t)(val >> 16);
+      }
+      off += pitch;
+    }
   }
 }
 
@@ -226,34 +251,34 @@ __global__ void __launch_bounds__(kBlendThreads) k_blend(const uint4 *__restrict
 }
 
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-                const uint32_t *col_lut, const uint32_t *row_lut, int grid_cols, int canvas_w, int canvas_h, int off_x,
-                int off_y, int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
-                int force_exact, cudaStream_t st) {
-  if (row0 < 0 || row1 > canvas_h || row0 > row1) return fail(APAP_E_BADARG, "warp: bad row band");
+                const uint32_t *col_lut, const uint32_t *row_groups, int n_groups, int grid_cols, int canvas_w,
+                int off_x, int off_y, int row0, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
+                size_t out_band_bytes, int force_exact, cudaStream_t st) {
   if ((long long)src_w * src_h > 2147483647LL)
     return fail(APAP_E_TOOBIG, "warp: source image has more than 2^31-1 pixels");
   if ((reinterpret_cast<uintptr_t>(cell_fast) & 15u) || (reinterpret_cast<uintptr_t>(col_lut) & 7u) ||
-      (reinterpret_cast<uintptr_t>(row_lut) & 7u))
-    return fail(APAP_E_ALIGN, "warp: cell_fast must be 16-byte, col_lut / row_lut 8-byte aligned");
-  if (row0 == row1) return 0;
+      (reinterpret_cast<uintptr_t>(row_groups) & 15u))
+    return fail(APAP_E_ALIGN, "warp: cell_fast / row_groups must be 16-byte, col_lut 8-byte aligned");
+  if (n_groups == 0) return 0;
+  if (out_band_bytes > 2147483647ULL) return fail(APAP_E_TOOBIG, "warp: row band larger than 2 GiB (split it)");
   WarpParams p;
   p.src = src; p.cell_fast = reinterpret_cast<const float4 *>(cell_fast); p.cell_hinv = cell_hinv;
-  p.col_lut = reinterpret_cast<const uint2 *>(col_lut); p.row_lut = reinterpret_cast<const uint2 *>(row_lut);
+  p.col_lut = reinterpret_cast<const uint2 *>(col_lut); p.row_groups = reinterpret_cast<const uint4 *>(row_groups);
   p.centre = centre; p.out = out_band;
-  p.row0 = row0; p.row1 = row1;
+  p.row0 = row0;
   p.chunks_per_row = (canvas_w + 31) / 32;
-  const long long n_warps = (long long)p.chunks_per_row * ((row1 - row0 + kRowsPerThread - 1) / kRowsPerThread);
+  const long long n_warps = (long long)p.chunks_per_row * n_groups;
   if (n_warps > 2147483647LL) return fail(APAP_E_TOOBIG, "warp: canvas band too large");
   p.n_warps = (int)n_warps;
   p.src_h = src_h; p.src_w = src_w; p.grid_cols = grid_cols; p.canvas_w = canvas_w;
   p.off_x = off_x; p.off_y = off_y; p.centre_h = centre_h; p.centre_w = centre_w; p.force_exact = force_exact;
-  p.word_stores = (canvas_w % 4 == 0) && !(reinterpret_cast<uintptr_t>(out_band) & 3u);
+  const bool words = (canvas_w % 4 == 0) && !(reinterpret_cast<uintptr_t>(out_band) & 3u);
   const unsigned blocks = (unsigned)((n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
   if (centre) {
-    if (p.word_stores) k_warp<true, true><<<blocks, kWarpThreads, 0, st>>>(p);
+    if (words) k_warp<true, true><<<blocks, kWarpThreads, 0, st>>>(p);
     else k_warp<true, false><<<blocks, kWarpThreads, 0, st>>>(p);
   } else {
-    if (p.word_stores) k_warp<false, true><<<blocks, kWarpThreads, 0, st>>>(p);
+    if (words) k_warp<false, true><<<blocks, kWarpThreads, 0, st>>>(p);
     else k_warp<false, false><<<blocks, kWarpThreads, 0, st>>>(p);
   }
   return check_cuda(cudaGetLastError(), "k_warp launch");

@@ -119,8 +119,8 @@ class ShardedAPAP:
         full[s.cell_row0:s.cell_row1] = local_h_rows
         src_dev = ori_img if not isinstance(ori_img, np.ndarray) else rt.to_device(torch, device, ori_img)
         tables = st.warp_tables_device(full, self.col_cell, self.row_cell, int(ori_img.shape[1]),
-                                       int(ori_img.shape[0]), device)
-        return st.warp_device(src_dev, tables, self.grid_cols, s.px_row0, s.px_row1)
+                                       int(ori_img.shape[0]), device, s.px_row0, s.px_row1)
+        return st.warp_device(src_dev, tables, self.grid_cols)
 
     def panorama(self, band, group=None):
         return gather_bands(band, self.shards, int(self.stitcher.final_width), group)

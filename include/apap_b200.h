@@ -34,6 +34,7 @@ extern "C" {
 #define APAP_KP_ROW     28   /* floats per keypoint row: 24 product terms, s*kx (x2), s*ky (x2)   */
 #define APAP_KP_CHUNK   128  /* keypoint rows per shared-memory stage; tables are padded to this  */
 #define APAP_HINV_ROW   12   /* floats per cell of the warp's fast-path record (see apap_warp)    */
+#define APAP_WARP_GROUP_ROWS 8 /* most canvas rows per row group of the warp kernel               */
 
 #define APAP_E_BADARG   (-1)
 #define APAP_E_ALIGN    (-2)
@@ -99,28 +100,35 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 
 /*
  * K3 -- mesh warp.  Replaces the pixel loop of APAP.local_warp (pyviz/apap.py:206-215): for the
- * canvas rows [row0, row1) looks the cell up (col_lut / row_lut = np.where(k < edges) of :207,:209),
- * applies that cell's H^-1 to (j - off_x, i - off_y, 1), divides, and copies
- * src[int(ty)][int(tx)] when 0 < tx < src_w and 0 < ty < src_h (else leaves 0).  Pixel selection
- * is bit-identical to the reference's float64 arithmetic: a float32 fast path on cell-relative
- * coefficients (cell_fast) decides every pixel whose coordinates are farther than the cell's
- * guard band eps from an integer, the rest are recomputed in float64 from cell_hinv.
+ * canvas rows covered by `row_groups` looks the cell up (col_lut / row_groups restate
+ * np.where(k < edges) of :207,:209), applies that cell's H^-1 to (j - off_x, i - off_y, 1), divides,
+ * and copies src[int(ty)][int(tx)] when 0 < tx < src_w and 0 < ty < src_h (else leaves 0).  Pixel
+ * selection is bit-identical to the reference's float64 arithmetic: a float32 fast path on
+ * cell-relative coefficients (cell_fast) decides every pixel whose coordinates are farther than the
+ * cell's guard band eps from an integer, the rest are recomputed in float64 from cell_hinv.
  *   cell_fast : float [grid_rows*grid_cols][APAP_HINV_ROW] = A0 B0 C0 A1 B1 C1 A2 B2 C2,
- *               int32 bits of (qbx - 0x4B400000), (qby - 0x4B400000), eps; with dx, dy the pixel's
- *               offset inside its cell:  src_x = qbx + floor((A0 dx + B0 dy + C0) / (A2 dx + B2 dy + C2))
+ *               int32 bits of (qbx - 0x4B400000), (qby - 0x4B400000), g; with dx, dy the pixel's
+ *               offset inside its cell:  src_x = qbx + floor((A0 dx + B0 dy + C0) / (A2 dx + B2 dy + C2));
+ *               g = 0.5 - eps (eps = the cell's guard band), g < 0 = the whole cell takes the float64
+ *               path, g > 1 = the whole cell maps outside the source image and is left black
  *   cell_hinv : float [grid_rows*grid_cols][9], the inverted grid of pyviz/apap.py:201-203
- *   col_lut   : uint32 [canvas_w] = cell column | dx << 16;  row_lut : uint32 [canvas_h] likewise
- *   out_band  : uint8 [(row1-row0)][canvas_w][3], 8-byte aligned; receives rows row0..row1-1
+ *   col_lut   : uint32 [canvas_w][2] = {cell column, float32 bits of dx}
+ *   row_groups: uint32 [n_groups][4] = {first canvas row, rows in the group (1..APAP_WARP_GROUP_ROWS),
+ *               cell row, float32 bits of dy of the first row}; a group never crosses a cell row; the
+ *               groups passed are the rows that get written (a row band of a sharded run = its groups)
+ *   row0      : canvas row stored at out_band[0]
+ *   out_band  : uint8 [rows][canvas_w][3], out_band_bytes < 2 GiB; when it is 4-byte aligned and
+ *               canvas_w % 4 == 0 the kernel uses packed 32-bit stores
  *   centre    : optional uint8 [centre_h][centre_w][3] pasted at (off_x, off_y) and blended with
  *               the warped pixel by the uniform_blend rule (fused K3+K4, pyviz/apap.py:259-261);
  *               NULL = plain warp
  *   force_exact : non-zero = every pixel takes the float64 path (validation switch)
  */
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-              const uint32_t *col_lut, const uint32_t *row_lut, int grid_cols,
-              int canvas_w, int canvas_h, int off_x, int off_y, int row0, int row1,
+              const uint32_t *col_lut, const uint32_t *row_groups, int n_groups, int grid_cols,
+              int canvas_w, int off_x, int off_y, int row0,
               const uint8_t *centre, int centre_h, int centre_w,
-              uint8_t *out_band, int force_exact, void *stream);
+              uint8_t *out_band, size_t out_band_bytes, int force_exact, void *stream);
 
 /*
  * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,

@@ -88,6 +88,24 @@ def test_cell_lookup_matches_reference_rule(golden):
         papap.cell_lookup_tables(mesh, fw, fh, 8, 8)
 
 
+def _rows_from_groups(groups, row_cell):
+    """Expand the kernel's row groups to per-row (cell row, dy) the way the kernel walks them, and
+    check that they tile the canvas rows exactly once without crossing a cell row."""
+    fh = row_cell.shape[0]
+    row_lut = np.zeros((fh, 2), dtype=np.uint32)
+    seen = np.zeros(fh, dtype=np.int64)
+    for i0, n, cr, dy0 in groups:
+        assert 1 <= n <= rt.WARP_GROUP_ROWS
+        rows = np.arange(int(i0), int(i0) + int(n))
+        seen[rows] += 1
+        assert (row_cell[rows] == cr).all()
+        dy = np.uint32(dy0).view(np.float32) + np.arange(int(n), dtype=np.float32)
+        row_lut[rows, 0] = cr
+        row_lut[rows, 1] = dy.astype(np.float32).view(np.uint32)
+    assert (seen == 1).all()
+    return row_lut
+
+
 def _emulate_fast_path(fast, col_lut, row_lut, gc, sw, sh, rng):
     """float32 fast path of k_warp (csrc/warp_blend.cu warp_row) in numpy: fma emulated through
     float64 (the product of two float32 is exact there; the double rounding is harmless at these
@@ -114,7 +132,8 @@ def _emulate_fast_path(fast, col_lut, row_lut, gc, sw, sh, rng):
     ix = np.where(clear, flx, 0).astype(np.int64) + bits[..., 0]
     iy = np.where(clear, fly, 0).astype(np.int64) + bits[..., 1]
     inb = (ix >= 0) & (ix < sw) & (iy >= 0) & (iy < sh)
-    return np.where(inb, iy * sw + ix, -1), ~clear
+    outside = r[..., 11] > 1.0                        # the kernel leaves these cells black without arithmetic
+    return np.where(inb & ~outside, iy * sw + ix, -1), ~clear & ~outside
 
 
 def _exact_path(inv_h, col, row, fw, fh, ox, oy, sw, sh):
@@ -145,7 +164,8 @@ def test_guard_band_makes_fast_path_exact(golden, name, scale):
         fh = min(fh, 600)
     mesh = apap_utils.get_mesh((fw, fh), sc.mesh_cells + 1)
     col, row = papap.cell_lookup_tables(mesh, fw, fh, sc.mesh_cells, sc.mesh_cells)
-    fast, col_lut, row_lut = papap.build_warp_tables(inv, col, row, ox, oy, sw, sh)
+    fast, col_lut, row_first = papap.build_warp_tables(inv, col, row, ox, oy, sw, sh)
+    row_lut = _rows_from_groups(papap.build_row_groups(row, row_first), row)
     assert fast.shape == (sc.mesh_cells ** 2, rt.HINV_ROW) and fast.dtype == np.float32
     assert np.array_equal(col_lut[:, 0], col) and np.array_equal(row_lut[:, 0], row)
     off, flagged = _emulate_fast_path(fast, col_lut, row_lut, sc.mesh_cells, sw, sh, np.random.default_rng(3))
@@ -154,6 +174,8 @@ def test_guard_band_makes_fast_path_exact(golden, name, scale):
     # cells of the stress case are ~750 px wide (quotients up to +-370), typical cells are 10-40 px
     assert flagged.mean() < (2e-4 if scale == 1.0 else 1e-2), flagged.mean()
     assert (want >= 0).mean() > 0.3        # the case does exercise in-bounds pixels
+    outside = fast[:, 11] > 1.0            # ... and whole cells outside the source image
+    assert 0.02 < outside.mean() < 0.6, outside.mean()
 
 
 def test_guard_band_adversarial_integer_hits():
@@ -169,12 +191,30 @@ def test_guard_band_adversarial_integer_hits():
         inv[..., 1, 2] = rng.integers(-5, 6, size=(8, 8))
         if trial >= 2:
             inv += (rng.standard_normal(inv.shape) * 10.0 ** -(trial + 3)).astype(np.float32)
-        fast, col_lut, row_lut = papap.build_warp_tables(inv, col, row, 11, 7, sw, sh)
+        fast, col_lut, row_first = papap.build_warp_tables(inv, col, row, 11, 7, sw, sh)
+        row_lut = _rows_from_groups(papap.build_row_groups(row, row_first), row)
         off, flagged = _emulate_fast_path(fast, col_lut, row_lut, 8, sw, sh, rng)
         want = _exact_path(inv, col, row, fw, fh, 11, 7, sw, sh)
         assert np.array_equal(off[~flagged], want[~flagged]), trial
         if trial < 2:
             assert flagged.all()
+
+
+def test_row_groups_bands_and_odd_luts():
+    """Bands of a sharded run get exactly their rows; runs are cut into near-equal groups; a lookup
+    table with repeated / non-monotone cell rows (mesh start > 0 wraps to the last cell) still tiles."""
+    row = np.repeat(np.arange(7), [11, 12, 3, 8, 9, 17, 1]).astype(np.uint16)
+    first = np.r_[0, np.cumsum([11, 12, 3, 8, 9, 17])]
+    g = papap.build_row_groups(row, first)
+    _rows_from_groups(g, row)
+    assert sorted(g[g[:, 2] == 5][:, 1].tolist()) == [5, 6, 6] and g[g[:, 2] == 3][:, 1].tolist() == [8]
+    band = papap.build_row_groups(row, first, 20, 45)
+    assert band[0, 0] == 20 and int(band[-1, 0] + band[-1, 1]) == 45 and band[:, 1].sum() == 25
+    assert np.uint32(band[0, 3]).view(np.float32) == 20 - 11          # dy of the band's first row inside cell row 1
+    assert papap.build_row_groups(row, first, 30, 30).shape == (0, 4)
+    wrapped = np.r_[np.full(4, 6), row].astype(np.uint16)               # rows 0..3 wrap to the last cell row
+    first_w = np.r_[4 + first[:6], 0]
+    _rows_from_groups(papap.build_row_groups(wrapped, first_w), wrapped)
 
 
 def test_guard_band_degenerate_cells_go_exact():
