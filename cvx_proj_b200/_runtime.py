@@ -17,7 +17,7 @@ GRAM_TERMS = 24
 KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
-WARP_GROUP_ROWS = 8
+WARP_BLOCK_ROWS = 4
 ABI_VERSION = 2
 EIG_AUTO = 0
 EIG_JACOBI = 1

@@ -25,9 +25,9 @@ from typing import NamedTuple
 import numpy as np
 
 from . import _runtime as rt
-from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW, WARP_GROUP_ROWS
+from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW, WARP_BLOCK_ROWS
 
-__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "build_row_groups", "cell_lookup_tables"]
+__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "build_row_blocks", "cell_lookup_tables"]
 
 _U = 2.0 ** -24          # float32 unit roundoff
 
@@ -133,7 +133,7 @@ def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndar
 
     ``col_lut[j] = (cell column, float32 bits of dx)`` with ``dx = j - (first canvas column of that
     cell)``; ``row_first[m]`` is the first canvas row of cell row m (``dy = i - row_first``, see
-    ``build_row_groups``).  ``cell_fast`` holds, per cell, the float32 fast path of
+    ``build_row_blocks``).  ``cell_fast`` holds, per cell, the float32 fast path of
     ``csrc/warp_blend.cu``: with ``(x0, y0)`` the cell's first pixel minus the canvas offsets, the
     reference's ``t = H^-1 [x0 + dx, y0 + dy, 1]`` (pyviz/apap.py:211-213) is rewritten as
 
@@ -223,31 +223,39 @@ def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndar
     return rec.reshape(gr * gc, HINV_ROW), col_lut, ilo
 
 
-def build_row_groups(row_cell: np.ndarray, row_first: np.ndarray, row0: int = 0, row1=None,
-                     max_rows: int = WARP_GROUP_ROWS) -> np.ndarray:
-    """Work list of the mesh warp for the canvas rows ``[row0, row1)``: ``uint32 [n_groups, 4]`` =
-    ``(first canvas row, rows in the group, cell row, float32 bits of dy of the first row)``.
+def build_row_blocks(row_cell: np.ndarray, row_first: np.ndarray, row0: int = 0, row1=None,
+                     max_rows: int = WARP_BLOCK_ROWS) -> np.ndarray:
+    """Work list of the mesh warp for the canvas rows ``[row0, row1)``: ``uint32 [n_blocks, 2]`` =
+    ``(first canvas row | rows << 28, cell row | dy of the first row << 16)``, in canvas order.
 
-    Every maximal run of canvas rows with the same cell row (``row_cell``, pyviz/apap.py:207) is cut
-    into ``ceil(len / max_rows)`` groups of near-equal height, so a group never crosses a cell row
-    and a lane of the kernel needs one cell record for all its pixels."""
+    Every maximal run of ``L`` canvas rows with the same cell row (``row_cell``, pyviz/apap.py:207) is
+    covered by ``ceil(L / max_rows)`` blocks that never cross a cell row, so a lane of the kernel
+    needs one cell record for all the pixels of a block.  Runs of at least ``max_rows`` rows get
+    FULL blocks only: their starts are spread evenly over ``[0, L - max_rows]`` and neighbouring
+    blocks overlap by a row where ``L`` is not a multiple (the overlapped rows are computed twice
+    and written twice with identical bytes), which keeps the kernel's hot path free of per-row
+    predicates.  ``dy`` is the first row's offset from the first canvas row of its cell row
+    (``row_first``, the origin of the warp records)."""
     row1 = row_cell.shape[0] if row1 is None else row1
     rc = row_cell[row0:row1].astype(np.int64)
     if rc.size == 0:
-        return np.zeros((0, 4), dtype=np.uint32)
+        return np.zeros((0, 2), dtype=np.uint32)
     starts = np.flatnonzero(np.r_[True, rc[1:] != rc[:-1]])
     lens = np.diff(np.r_[starts, rc.size])
-    parts = -(-lens // max_rows)                                  # groups per run
-    run = np.repeat(np.arange(starts.size), parts)                 # run index of every group
-    k = np.arange(run.size) - np.repeat(np.cumsum(parts) - parts, parts)     # group index inside its run
-    lo = starts[run] + (k * lens[run]) // parts[run]
-    hi = starts[run] + ((k + 1) * lens[run]) // parts[run]
-    groups = np.empty((run.size, 4), dtype=np.uint32)
-    groups[:, 0] = lo + row0
-    groups[:, 1] = hi - lo
-    groups[:, 2] = rc[lo]
-    groups[:, 3] = (lo + row0 - row_first[rc[lo]]).astype(np.float32).view(np.uint32)
-    return groups
+    parts = -(-lens // max_rows)                                  # blocks per run
+    run = np.repeat(np.arange(starts.size), parts)                 # run index of every block
+    k = np.arange(run.size) - np.repeat(np.cumsum(parts) - parts, parts)     # block index inside its run
+    span = np.maximum(lens[run] - max_rows, 0)                     # last admissible start of a full block
+    lo = starts[run] + (k * span + (parts[run] - 1) // 2) // np.maximum(parts[run] - 1, 1)
+    rows = np.minimum(lens[run], max_rows)
+    first = lo + row0
+    dy = first - row_first[rc[lo]]
+    if first.max(initial=0) >= 1 << 28 or dy.max(initial=0) >= 1 << 16 or dy.min(initial=0) < 0:
+        raise ValueError("warp: canvas taller than 2^28 rows or a cell row spanning more than 65535 canvas rows")
+    blocks = np.empty((run.size, 2), dtype=np.uint32)
+    blocks[:, 0] = first | (rows << 28)
+    blocks[:, 1] = rc[lo] | (dy << 16)
+    return blocks
 
 
 class _PinnedStage:
@@ -281,13 +289,13 @@ class _PinnedStage:
 
 class WarpTables(NamedTuple):
     """Device-resident inputs of ``apap_warp`` for one inverted grid and one band of canvas rows
-    (see ``build_warp_tables`` / ``build_row_groups``)."""
+    (see ``build_warp_tables`` / ``build_row_blocks``)."""
     cell_fast: object       # float32 [cells * 12]
     cell_hinv: object       # float32 [cells * 9]
     col_lut: object         # int32 [canvas_w * 2]
-    row_groups: object      # int32 [n_groups * 4]
-    n_groups: int
-    row0: int               # the band of canvas rows the groups cover
+    row_blocks: object      # int32 [n_blocks * 2]
+    n_blocks: int
+    row0: int               # the band of canvas rows the blocks cover
     row1: int
     exact_cells_frac: float  # share of cells whose every pixel takes the float64 path
 
@@ -535,19 +543,19 @@ class APAP:
         return hit
 
     def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None, row0=0, row1=None):
-        """Build the warp kernel's tables (``build_warp_tables`` + ``build_row_groups`` for the canvas
+        """Build the warp kernel's tables (``build_warp_tables`` + ``build_row_blocks`` for the canvas
         rows ``[row0, row1)``) for an inverted grid and upload them with one host->device copy."""
         torch, device = rt.torch_cuda(device if device is not None else self.device)
         row1 = int(self.final_height) if row1 is None else row1
         fast, col_lut, row_first = build_warp_tables(inv_h, col_cell, row_cell, int(self.offset_x),
                                                      int(self.offset_y), int(src_w), int(src_h))
-        groups = build_row_groups(row_cell, row_first, row0, row1)
+        blocks = build_row_blocks(row_cell, row_first, row0, row1)
         hinv = np.ascontiguousarray(inv_h, dtype=np.float32).reshape(-1, 9)
         if not hasattr(self, "_warp_stage"):
             self._warp_stage = _PinnedStage()
-        views = self._warp_stage.upload(torch, device, (fast, hinv, col_lut, groups))
+        views = self._warp_stage.upload(torch, device, (fast, hinv, col_lut, blocks))
         return WarpTables(views[0].view(torch.float32), views[1].view(torch.float32),
-                          views[2].view(torch.int32), views[3].view(torch.int32), int(groups.shape[0]),
+                          views[2].view(torch.int32), views[3].view(torch.int32), int(blocks.shape[0]),
                           int(row0), int(row1), float((fast[:, 11] < 0).mean()))
 
     def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False):
@@ -562,8 +570,8 @@ class APAP:
         with torch.cuda.device(device):
             rt.check(lib.apap_warp(
                 src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
-                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_groups.data_ptr(),
-                tables.n_groups, grid_cols, fw, int(self.offset_x), int(self.offset_y), tables.row0,
+                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_blocks.data_ptr(),
+                tables.n_blocks, grid_cols, fw, int(self.offset_x), int(self.offset_y), tables.row0,
                 centre_dev.data_ptr() if centre_dev is not None else None, ch, cw, out.data_ptr(),
                 out.numel(), int(force_exact), rt.stream_ptr(torch, device)), "apap_warp")
         return out

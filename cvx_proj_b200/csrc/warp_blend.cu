@@ -2,16 +2,19 @@
 // fused with K4, and K4 -- uniform_blend (pyviz/apap_utils.py:75-88).
 //
 // HBM-bound byte work: every canvas pixel is written once (3 B), every source pixel is read at
-// most once from HBM.  Work unit: a warp owns 32 consecutive canvas columns x one "row group" =
-// up to 8 consecutive canvas rows of ONE cell row (the host cuts every cell row into such
-// groups), so a lane (= one column) needs exactly one cell record for all its pixels and the
-// whole index computation is straight-line code.  In every row the 32 lanes gather ~96
-// contiguous source bytes (1-2 L1 wavefronts per byte plane instead of one line per lane) and
-// their 32 pixels are 96 contiguous output bytes, which the warp re-packs with two shuffles +
-// one byte-permute into 24 aligned 32-bit stores.  Three phases per warp so that all of a
-// lane's gathers are in flight together: (1) source index of every row on packed FP32x2
-// arithmetic, two rows per instruction, (2) issue every byte load, (3) combine, blend,
-// re-pack, store.
+// most once from HBM.  The host cuts the canvas rows into "row blocks" of at most 4 rows that
+// never cross a cell row.  A warp owns 32 consecutive canvas columns (lane = column) and walks a
+// strip of consecutive row blocks downwards, so everything that depends on the column only -- the
+// cell column, dx, the store lane pattern -- is loop invariant, and a lane needs one cell record
+// per block (reloaded only when the strip enters a new cell row).  Per block, three phases:
+//   1. source pixel index of the 4 rows on packed FP32x2 arithmetic (two rows per instruction),
+//      straight-line; pixels inside the guard band are flagged and re-decided in float64 after it;
+//   2. issue the 12 byte gathers of the lane (the 32 lanes of a row read ~96 contiguous source
+//      bytes: 1-2 L1 wavefronts per byte plane);
+//   3. combine, blend, re-pack the warp's 96 output bytes of a row into 24 aligned 32-bit stores
+//      with two shuffles + one byte-permute.
+// The loop is software pipelined: phases 1-2 of block t+1 are issued before phase 3 of block t, so
+// two blocks' gathers are in flight per lane while the previous block is stored.
 //
 // Pixel selection must equal the reference's float64 arithmetic (float32 H^-1 promoted to
 // float64, divide, strict bounds, truncate).  The float32 fast path works in cell-relative
@@ -21,28 +24,27 @@
 // float32 error is ~1e-5 px:   src_x = qbx + floor((A0 dx + B0 dy + C0) / (A2 dx + B2 dy + C2)).
 // The host also supplies, per cell, a rigorous bound eps on that error.  A quotient farther than
 // eps from every integer has the same floor and the same bounds decision in both arithmetics;
-// the others (~1e-4 of the pixels) are flagged and recomputed in float64 exactly as the
-// reference does, after the straight-line part.
+// the others (~1e-4 of the pixels) are recomputed in float64 exactly as the reference does.
 #include "common.cuh"
 
 namespace apap {
 
 constexpr int kWarpThreads = 256;
 constexpr int kWarpsPerCta = kWarpThreads / 32;
-constexpr int kRowsPerGroup = APAP_WARP_GROUP_ROWS;   // even: rows are processed in pairs
-static_assert(kRowsPerGroup % 2 == 0, "rows are processed in pairs");
+constexpr int kBlockRows = APAP_WARP_BLOCK_ROWS;      // rows per row block (processed as 2 pairs)
+static_assert(kBlockRows == 4, "the kernel processes a row block as two row pairs");
 
 struct WarpParams {
   const uint8_t *src;
   const float4 *cell_fast;     // [cells][3] float4: A0 B0 C0 A1 | B1 C1 A2 B2 | C2 qbx' qby' (int bits) g
   const float *cell_hinv;      // [cells][9]: the reference's inverted grid (float64 path only)
   const uint2 *col_lut;        // [canvas_w]: {cell column, float bits of x - cell's first x}
-  const uint4 *row_groups;     // [n_groups]: {first canvas row, rows (1..8), cell row, float bits of dy of the first row}
+  const uint2 *row_blocks;     // [n_blocks]: {first canvas row | rows << 28, cell row | dy of the first row << 16}
   const uint8_t *centre;
   uint8_t *out;                // first byte of canvas row `row0`
   int row0;                    // first canvas row of the band `out` holds
+  int n_blocks;
   int chunks_per_row;          // ceil(canvas_w / 32)
-  int n_warps;                 // chunks_per_row * n_groups
   int src_h, src_w;
   int grid_cols;
   int canvas_w;
@@ -66,48 +68,61 @@ __device__ __noinline__ int exact_lookup(const float *__restrict__ h, int x, int
   return -1;
 }
 
-// kWords: the band's rows are 4-byte aligned (canvas_w % 4 == 0): the warp's 32 pixels of a row
-// leave as 24 packed 32-bit stores; otherwise three byte stores per lane.
-template <bool kBlend, bool kWords>
-__global__ void __launch_bounds__(kWarpThreads) k_warp(const WarpParams p) {
-  constexpr int P = kRowsPerGroup;
-  const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (wid >= p.n_warps) return;                    // warp-uniform
-  const int g = wid / p.chunks_per_row;
-  const int j0 = (wid - g * p.chunks_per_row) * 32;
-  const uint4 grp = __ldg(p.row_groups + g);       // same address in every lane
-  const int i0 = (int)grp.x, n_rows = (int)grp.y;
-  const int j = j0 + lane;
-  const bool col_ok = j < p.canvas_w;
-  const uint2 cl = __ldg(p.col_lut + (col_ok ? j : p.canvas_w - 1));
-  const int cell = (int)grp.z * p.grid_cols + (int)cl.x;
-  const float4 *rec = p.cell_fast + (size_t)cell * 3;
-  const float4 u = __ldg(rec), v = __ldg(rec + 1), w = __ldg(rec + 2);
-  const int x = j - p.off_x, y0 = i0 - p.off_y;
+// Per-lane state of the cell the strip is currently in.
+struct CellState {
+  float b0, b1, b2, m0, m1, m2, hme;
+  int qbx, qby;                // integer base - bits(kMagic)
+  int cell_row, cell;
+  bool outside;                // every pixel of the cell maps outside the source
+};
+
+// Enter the cell row of a block: (re)load the lane's cell record when it changes (warp-uniform).
+__device__ __forceinline__ void enter_cell_row(const WarpParams &p, const uint2 cl, float dxf, int cell_row,
+                                               CellState &c) {
+  if (cell_row != c.cell_row) {
+    c.cell_row = cell_row;
+    c.cell = cell_row * p.grid_cols + (int)cl.x;
+    const float4 *rec = p.cell_fast + (size_t)c.cell * 3;
+    const float4 u = __ldg(rec), v = __ldg(rec + 1), w = __ldg(rec + 2);
+    c.m0 = fmaf(u.x, dxf, u.z); c.b0 = u.y;
+    c.m1 = fmaf(u.w, dxf, v.y); c.b1 = v.x;
+    c.m2 = fmaf(v.z, dxf, w.x); c.b2 = v.w;
+    c.qbx = __float_as_int(w.y);
+    c.qby = __float_as_int(w.z);
+    // g = 0.5 - eps; a record with g < 0 (degenerate cell, forced) never passes; NaN never passes
+    c.hme = p.force_exact ? -1.f : w.w;
+    c.outside = w.w > 1.f && !p.force_exact;
+  }
+}
+
+// Phases 1 + 2 of one row block of one lane: the source pixel index of every row, then all byte
+// gathers issued together.  kFull: the block has exactly kBlockRows rows (the host makes every
+// block full unless its cell row has fewer canvas rows than that): straight-line code; the
+// partial form predicates each row on n_rows.
+template <bool kBlend, bool kFull>
+__device__ __forceinline__ void block_issue(const WarpParams &p, const uint8_t *__restrict__ src, int i0, int n_rows,
+                                            float dy0, int x, bool col_ok, const CellState &c,
+                                            uint32_t (&b0)[kBlockRows], uint32_t (&b1)[kBlockRows],
+                                            uint32_t (&b2)[kBlockRows], uint32_t (&c0)[kBlockRows],
+                                            uint32_t (&c1)[kBlockRows], uint32_t (&c2)[kBlockRows]) {
+  constexpr int P = kBlockRows;
+  const int y0 = i0 - p.off_y;
 
   // ---- phase 1: source pixel index of every row (-1 = leave black) ---------------------------
   int idx[P];
-  const bool outside = w.w > 1.f && !p.force_exact;          // the whole cell maps outside the source
-  if (__all_sync(0xffffffffu, outside)) {
+  if (__all_sync(0xffffffffu, c.outside)) {
 #pragma unroll
     for (int k = 0; k < P; ++k) idx[k] = -1;
   } else {
-    const float dxf = __uint_as_float(cl.y), dy0 = __uint_as_float(grp.w);
-    const float m0 = fmaf(u.x, dxf, u.z), m1 = fmaf(u.w, dxf, v.y), m2 = fmaf(v.z, dxf, w.x);
-    const float b0 = u.y, b1 = v.x, b2 = v.w;
-    const int qbx = __float_as_int(w.y), qby = __float_as_int(w.z);   // integer base - bits(kMagic)
-    // g = 0.5 - eps; a record with g < 0 (degenerate cell, forced) never passes; NaN never passes
-    const float hme = p.force_exact ? -1.f : w.w;
     const float2 km = make_float2(kMagic, kMagic), nkm = make_float2(-kMagic, -kMagic), nh = make_float2(-0.5f, -0.5f);
     unsigned flagged = 0;                           // rows whose quotient is inside the guard band
 #pragma unroll
     for (int k = 0; k < P; k += 2) {
       // two rows at once on packed FP32x2 arithmetic (identical roundings to the scalar form)
       const float2 dy = make_float2(dy0 + (float)k, dy0 + (float)(k + 1));
-      const float2 n0 = __ffma2_rn(make_float2(b0, b0), dy, make_float2(m0, m0));
-      const float2 n1 = __ffma2_rn(make_float2(b1, b1), dy, make_float2(m1, m1));
-      const float2 d = __ffma2_rn(make_float2(b2, b2), dy, make_float2(m2, m2));
+      const float2 n0 = __ffma2_rn(make_float2(c.b0, c.b0), dy, make_float2(c.m0, c.m0));
+      const float2 n1 = __ffma2_rn(make_float2(c.b1, c.b1), dy, make_float2(c.m1, c.m1));
+      const float2 d = __ffma2_rn(make_float2(c.b2, c.b2), dy, make_float2(c.m2, c.m2));
       const float2 r = make_float2(rcp_approx(d.x), rcp_approx(d.y));
       const float2 qx = __fmul2_rn(n0, r), qy = __fmul2_rn(n1, r);
       const float2 tx = __fadd2_rd(qx, km), ty = __fadd2_rd(qy, km);             // floor + kMagic
@@ -119,68 +134,64 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp(const WarpParams p) {
       for (int e = 0; e < 2; ++e) {
         const float txe = e ? tx.y : tx.x, tye = e ? ty.y : ty.x;
         const float hxe = e ? hx.y : hx.x, hye = e ? hy.y : hy.x;
-        const bool clear = fmaxf(fabsf(hxe), fabsf(hye)) <= hme;
-        const int ix = __float_as_int(txe) + qbx;
-        const int iy = __float_as_int(tye) + qby;
+        const bool clear = fmaxf(fabsf(hxe), fabsf(hye)) <= c.hme;
+        const int ix = __float_as_int(txe) + c.qbx;
+        const int iy = __float_as_int(tye) + c.qby;
         const bool inb = ((unsigned)ix < (unsigned)p.src_w) & ((unsigned)iy < (unsigned)p.src_h);
-        idx[k + e] = (inb && !outside) ? iy * p.src_w + ix : -1;
-        if (!clear && !outside) flagged |= 1u << (k + e);
+        idx[k + e] = (inb && !c.outside) ? iy * p.src_w + ix : -1;
+        if (!clear && !c.outside) flagged |= 1u << (k + e);
       }
     }
-    flagged &= (1u << n_rows) - 1u;
+    if (!kFull) flagged &= (1u << n_rows) - 1u;
     if (__any_sync(0xffffffffu, flagged != 0)) {    // rare: re-decide the flagged pixels in float64
-      const float *h = p.cell_hinv + (size_t)cell * 9;
+      const float *h = p.cell_hinv + (size_t)c.cell * 9;
 #pragma unroll
       for (int k = 0; k < P; ++k)
         if (flagged & (1u << k)) idx[k] = exact_lookup(h, x, y0 + k, p.src_w, p.src_h);
     }
-#pragma unroll
-    for (int k = 0; k < P; ++k)
-      if (k >= n_rows) idx[k] = -1;
   }
 
-  // ---- phase 2: every byte load of the lane in flight together --------------------------------
-  const uint8_t *__restrict__ src = p.src;
-  uint32_t b0[P], b1[P], b2[P];
+  // ---- phase 2: every byte load of the block in flight together -------------------------------
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     b0[k] = b1[k] = b2[k] = 0;
-    if (idx[k] >= 0) {
+    if (idx[k] >= 0 && (kFull || k < n_rows)) {
       const uint8_t *q = src + (size_t)(unsigned)idx[k] * 3;
       b0[k] = __ldg(q); b1[k] = __ldg(q + 1); b2[k] = __ldg(q + 2);
     }
   }
-  uint32_t c0[kBlend ? P : 1], c1[kBlend ? P : 1], c2[kBlend ? P : 1];
   if (kBlend) {
     // centre image pasted at (off_x, off_y) (pyviz/apap.py:259-260)
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       const int cy = y0 + k;
       c0[k] = c1[k] = c2[k] = 0;
-      if (k < n_rows && (unsigned)cy < (unsigned)p.centre_h && (unsigned)x < (unsigned)p.centre_w && col_ok) {
+      if ((kFull || k < n_rows) && (unsigned)cy < (unsigned)p.centre_h && (unsigned)x < (unsigned)p.centre_w && col_ok) {
         const uint8_t *q = p.centre + ((size_t)cy * p.centre_w + x) * 3;
         c0[k] = __ldg(q); c1[k] = __ldg(q + 1); c2[k] = __ldg(q + 2);
       }
     }
   }
+}
 
-  // ---- phase 3: combine, blend, re-pack across the warp, store --------------------------------
-  // kWords: output word w = lane (< 24) takes its 4 bytes from the pixels of lanes lane_a = (4w)/3
-  // and lane_a + 1, starting at byte (4w) % 3 of the first
-  const int lane_a = (lane + lane / 3) & 31, lane_b = (lane_a + 1) & 31;
-  const uint32_t sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
-  const bool store_ok = kWords ? lane < min(24, (3 * (p.canvas_w - j0)) >> 2) : col_ok;
-  const uint32_t pitch = (uint32_t)p.canvas_w * 3u;                 // the band is < 2^31 bytes (launch_warp)
-  uint32_t off = ((uint32_t)(i0 - p.row0) * (uint32_t)p.canvas_w + (uint32_t)j0) * 3u + (kWords ? 4u : 3u) * lane;
+// Phase 3 of one row block: combine, blend, re-pack across the warp, store.
+// kWords: the band's rows are 4-byte aligned (canvas_w % 4 == 0): the warp's 32 pixels of a row
+// leave as 24 packed 32-bit stores; otherwise three byte stores per lane.
+template <bool kBlend, bool kWords, bool kFull>
+__device__ __forceinline__ void block_store(const WarpParams &p, int i0, int n_rows, const uint32_t (&b0)[kBlockRows],
+                                            const uint32_t (&b1)[kBlockRows], const uint32_t (&b2)[kBlockRows],
+                                            const uint32_t (&c0)[kBlockRows], const uint32_t (&c1)[kBlockRows],
+                                            const uint32_t (&c2)[kBlockRows], uint32_t lane_off, uint32_t pitch,
+                                            int lane_a, int lane_b, uint32_t sel, bool store_ok) {
+  uint8_t *d = p.out + ((uint32_t)(i0 - p.row0) * pitch + lane_off);   // the band is < 2^31 bytes (launch_warp)
 #pragma unroll
-  for (int k = 0; k < P; ++k) {
-    if (k < n_rows) {                              // warp-uniform
+  for (int k = 0; k < kBlockRows; ++k) {
+    if (kFull || k < n_rows) {                     // warp-uniform
       uint32_t val = __byte_perm(__byte_perm(b0[k], b1[k], 0x1140), b2[k], 0x3410);   // b0 | b1<<8 | b2<<16
       if (kBlend) {                                // uniform_blend (pyviz/apap_utils.py:75-88)
         const uint32_t cv = __byte_perm(__byte_perm(c0[k], c1[k], 0x1140), c2[k], 0x3410);
         if (cv != 0) val = (val != 0) ? __vhaddu4(val, cv) : cv;
       }
-      uint8_t *d = p.out + off;
       if (kWords) {
         const uint32_t va = __shfl_sync(0xffffffffu, val, lane_a);
         const uint32_t vb = __shfl_sync(0xffffffffu, val, lane_b);
@@ -190,7 +201,82 @@ __global__ void __launch_bounds__(kWarpThreads) k_warp(const WarpParams p) {
         d[1] = (uint8_t)(val >> 8);
         d[2] = (uint8_t)(val >> 16);
       }
-      off += pitch;
+      d += pitch;
+    }
+  }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+
+// grid.x = groups of 8 column chunks (one per warp of the CTA), grid.y = S "lanes" of strips: the
+// warp (chunk, s) visits the block pairs s, s + S, s + 2S, ... of the band, so every warp samples
+// the whole height of the canvas (mapped and unmapped regions alike -> even load) while its
+// column state stays loop invariant.  The cell record of the next visit is prefetched into L1
+// while the current visit's gathers are in flight.
+template <bool kBlend, bool kWords>
+__global__ void __launch_bounds__(kWarpThreads, 4) k_warp(const WarpParams p) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (chunk >= p.chunks_per_row) return;           // warp-uniform
+  const int j0 = chunk * 32;
+
+  // column-only state: loop invariant
+  const int j = j0 + lane;
+  const bool col_ok = j < p.canvas_w;
+  const uint2 cl = __ldg(p.col_lut + (col_ok ? j : p.canvas_w - 1));
+  const float dxf = __uint_as_float(cl.y);
+  const int x = j - p.off_x;
+  const uint8_t *__restrict__ src = p.src;
+  // kWords: output word w = lane (< 24) takes its 4 bytes from the pixels of lanes lane_a = (4w)/3
+  // and lane_a + 1, starting at byte (4w) % 3 of the first
+  const int lane_a = (lane + lane / 3) & 31, lane_b = (lane_a + 1) & 31;
+  const uint32_t sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
+  const bool store_ok = kWords ? lane < min(24, (3 * (p.canvas_w - j0)) >> 2) : col_ok;
+  const uint32_t pitch = (uint32_t)p.canvas_w * 3u;
+  const uint32_t lane_off = (uint32_t)j0 * 3u + (kWords ? 4u : 3u) * lane;
+
+  CellState c;
+  c.b0 = c.b1 = c.b2 = c.m0 = c.m1 = 0.f; c.m2 = 1.f; c.hme = -1.f;
+  c.qbx = c.qby = 0; c.cell_row = -1; c.cell = 0; c.outside = false;
+
+  const int stride = gridDim.y * 2;
+  int t = blockIdx.y * 2;
+  if (t >= p.n_blocks) return;
+  uint2 nxt0 = __ldg(p.row_blocks + t), nxt1 = __ldg(p.row_blocks + min(t + 1, p.n_blocks - 1));
+  for (; t < p.n_blocks; t += stride) {
+    const uint2 cur0 = nxt0, cur1 = nxt1;
+    if (t + stride < p.n_blocks) {                 // the next visit's entries: in flight during this one
+      nxt0 = __ldg(p.row_blocks + t + stride);
+      nxt1 = __ldg(p.row_blocks + min(t + stride + 1, p.n_blocks - 1));
+    }
+    const int i0a = (int)(cur0.x & 0x0fffffffu), na = (int)(cur0.x >> 28);
+    const int i0b = (int)(cur1.x & 0x0fffffffu), nb = (t + 1 < p.n_blocks) ? (int)(cur1.x >> 28) : 0;
+    uint32_t a0[kBlockRows], a1[kBlockRows], a2[kBlockRows], ca0[kBlockRows], ca1[kBlockRows], ca2[kBlockRows];
+    if (na == kBlockRows && nb == kBlockRows) {    // warp-uniform: the hot, straight-line path
+      enter_cell_row(p, cl, dxf, (int)(cur0.y & 0xffffu), c);
+      block_issue<kBlend, true>(p, src, i0a, na, (float)(cur0.y >> 16), x, col_ok, c, a0, a1, a2, ca0, ca1, ca2);
+      // the record the next visit starts with: into L1 while this visit's gathers are in flight
+      if (t + stride < p.n_blocks) {
+        const char *rec = reinterpret_cast<const char *>(p.cell_fast) +
+                          ((size_t)((int)(nxt0.y & 0xffffu) * p.grid_cols + (int)cl.x)) * 48;
+        prefetch_l1(rec);
+        prefetch_l1(rec + 32);
+      }
+      block_store<kBlend, kWords, true>(p, i0a, na, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+      enter_cell_row(p, cl, dxf, (int)(cur1.y & 0xffffu), c);
+      block_issue<kBlend, true>(p, src, i0b, nb, (float)(cur1.y >> 16), x, col_ok, c, a0, a1, a2, ca0, ca1, ca2);
+      block_store<kBlend, kWords, true>(p, i0b, nb, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+    } else {                                       // partial blocks (cell rows shorter than 4 canvas rows, band end)
+      enter_cell_row(p, cl, dxf, (int)(cur0.y & 0xffffu), c);
+      block_issue<kBlend, false>(p, src, i0a, na, (float)(cur0.y >> 16), x, col_ok, c, a0, a1, a2, ca0, ca1, ca2);
+      block_store<kBlend, kWords, false>(p, i0a, na, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+      if (nb > 0) {
+        enter_cell_row(p, cl, dxf, (int)(cur1.y & 0xffffu), c);
+        block_issue<kBlend, false>(p, src, i0b, nb, (float)(cur1.y >> 16), x, col_ok, c, a0, a1, a2, ca0, ca1, ca2);
+        block_store<kBlend, kWords, false>(p, i0b, nb, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+      }
     }
   }
 }
@@ -251,35 +337,40 @@ __global__ void __launch_bounds__(kBlendThreads) k_blend(const uint4 *__restrict
 }
 
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-                const uint32_t *col_lut, const uint32_t *row_groups, int n_groups, int grid_cols, int canvas_w,
+                const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w,
                 int off_x, int off_y, int row0, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
                 size_t out_band_bytes, int force_exact, cudaStream_t st) {
   if ((long long)src_w * src_h > 2147483647LL)
     return fail(APAP_E_TOOBIG, "warp: source image has more than 2^31-1 pixels");
   if ((reinterpret_cast<uintptr_t>(cell_fast) & 15u) || (reinterpret_cast<uintptr_t>(col_lut) & 7u) ||
-      (reinterpret_cast<uintptr_t>(row_groups) & 15u))
-    return fail(APAP_E_ALIGN, "warp: cell_fast / row_groups must be 16-byte, col_lut 8-byte aligned");
-  if (n_groups == 0) return 0;
+      (reinterpret_cast<uintptr_t>(row_blocks) & 7u))
+    return fail(APAP_E_ALIGN, "warp: cell_fast must be 16-byte, col_lut / row_blocks 8-byte aligned");
+  if (n_blocks == 0) return 0;
   if (out_band_bytes > 2147483647ULL) return fail(APAP_E_TOOBIG, "warp: row band larger than 2 GiB (split it)");
   WarpParams p;
   p.src = src; p.cell_fast = reinterpret_cast<const float4 *>(cell_fast); p.cell_hinv = cell_hinv;
-  p.col_lut = reinterpret_cast<const uint2 *>(col_lut); p.row_groups = reinterpret_cast<const uint4 *>(row_groups);
+  p.col_lut = reinterpret_cast<const uint2 *>(col_lut); p.row_blocks = reinterpret_cast<const uint2 *>(row_blocks);
   p.centre = centre; p.out = out_band;
   p.row0 = row0;
+  p.n_blocks = n_blocks;
   p.chunks_per_row = (canvas_w + 31) / 32;
-  const long long n_warps = (long long)p.chunks_per_row * n_groups;
-  if (n_warps > 2147483647LL) return fail(APAP_E_TOOBIG, "warp: canvas band too large");
-  p.n_warps = (int)n_warps;
   p.src_h = src_h; p.src_w = src_w; p.grid_cols = grid_cols; p.canvas_w = canvas_w;
   p.off_x = off_x; p.off_y = off_y; p.centre_h = centre_h; p.centre_w = centre_w; p.force_exact = force_exact;
   const bool words = (canvas_w % 4 == 0) && !(reinterpret_cast<uintptr_t>(out_band) & 3u);
-  const unsigned blocks = (unsigned)((n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
+  // one resident wave: grid.x CTAs side by side cover the canvas width, grid.y of them share its height
+  const int gx = (p.chunks_per_row + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int visits = (n_blocks + 1) / 2;           // a visit = two consecutive row blocks
+  int gy = (sm_count_cached() * 4) / gx;           // 4 CTAs of 8 warps resident per SM (launch bounds)
+  if (gy < 1) gy = 1;
+  if (gy > visits) gy = visits;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid(gx, gy);
   if (centre) {
-    if (words) k_warp<true, true><<<blocks, kWarpThreads, 0, st>>>(p);
-    else k_warp<true, false><<<blocks, kWarpThreads, 0, st>>>(p);
+    if (words) k_warp<true, true><<<grid, kWarpThreads, 0, st>>>(p);
+    else k_warp<true, false><<<grid, kWarpThreads, 0, st>>>(p);
   } else {
-    if (words) k_warp<false, true><<<blocks, kWarpThreads, 0, st>>>(p);
-    else k_warp<false, false><<<blocks, kWarpThreads, 0, st>>>(p);
+    if (words) k_warp<false, true><<<grid, kWarpThreads, 0, st>>>(p);
+    else k_warp<false, false><<<grid, kWarpThreads, 0, st>>>(p);
   }
   return check_cuda(cudaGetLastError(), "k_warp launch");
 }

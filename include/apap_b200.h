@@ -34,7 +34,7 @@ extern "C" {
 #define APAP_KP_ROW     28   /* floats per keypoint row: 24 product terms, s*kx (x2), s*ky (x2)   */
 #define APAP_KP_CHUNK   128  /* keypoint rows per shared-memory stage; tables are padded to this  */
 #define APAP_HINV_ROW   12   /* floats per cell of the warp's fast-path record (see apap_warp)    */
-#define APAP_WARP_GROUP_ROWS 8 /* most canvas rows per row group of the warp kernel               */
+#define APAP_WARP_BLOCK_ROWS 4 /* most canvas rows per row block of the warp kernel               */
 
 #define APAP_E_BADARG   (-1)
 #define APAP_E_ALIGN    (-2)
@@ -100,7 +100,7 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 
 /*
  * K3 -- mesh warp.  Replaces the pixel loop of APAP.local_warp (pyviz/apap.py:206-215): for the
- * canvas rows covered by `row_groups` looks the cell up (col_lut / row_groups restate
+ * canvas rows covered by `row_blocks` looks the cell up (col_lut / row_blocks restate
  * np.where(k < edges) of :207,:209), applies that cell's H^-1 to (j - off_x, i - off_y, 1), divides,
  * and copies src[int(ty)][int(tx)] when 0 < tx < src_w and 0 < ty < src_h (else leaves 0).  Pixel
  * selection is bit-identical to the reference's float64 arithmetic: a float32 fast path on
@@ -113,9 +113,10 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
  *               path, g > 1 = the whole cell maps outside the source image and is left black
  *   cell_hinv : float [grid_rows*grid_cols][9], the inverted grid of pyviz/apap.py:201-203
  *   col_lut   : uint32 [canvas_w][2] = {cell column, float32 bits of dx}
- *   row_groups: uint32 [n_groups][4] = {first canvas row, rows in the group (1..APAP_WARP_GROUP_ROWS),
- *               cell row, float32 bits of dy of the first row}; a group never crosses a cell row; the
- *               groups passed are the rows that get written (a row band of a sharded run = its groups)
+ *   row_blocks: uint32 [n_blocks][2] = {first canvas row | rows << 28 (rows = 1..APAP_WARP_BLOCK_ROWS),
+ *               cell row | dy of the first row << 16}, in canvas order; a block never crosses a cell
+ *               row; the blocks passed are the rows that get written (a row band of a sharded run =
+ *               its blocks); canvas rows < 2^28, cell rows and dy < 2^16
  *   row0      : canvas row stored at out_band[0]
  *   out_band  : uint8 [rows][canvas_w][3], out_band_bytes < 2 GiB; when it is 4-byte aligned and
  *               canvas_w % 4 == 0 the kernel uses packed 32-bit stores
@@ -125,7 +126,7 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
  *   force_exact : non-zero = every pixel takes the float64 path (validation switch)
  */
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-              const uint32_t *col_lut, const uint32_t *row_groups, int n_groups, int grid_cols,
+              const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols,
               int canvas_w, int off_x, int off_y, int row0,
               const uint8_t *centre, int centre_h, int centre_w,
               uint8_t *out_band, size_t out_band_bytes, int force_exact, void *stream);

@@ -88,22 +88,29 @@ def test_cell_lookup_matches_reference_rule(golden):
         papap.cell_lookup_tables(mesh, fw, fh, 8, 8)
 
 
-def _rows_from_groups(groups, row_cell):
-    """Expand the kernel's row groups to per-row (cell row, dy) the way the kernel walks them, and
-    check that they tile the canvas rows exactly once without crossing a cell row."""
+def _rows_from_blocks(blocks, row_cell, row_first, row0=0):
+    """Expand the kernel's row blocks to per-row (cell row, dy) the way the kernel walks them, and
+    check the invariants: canvas order, no block crosses a cell row, blocks are full (4 rows) unless
+    the whole run is shorter, overlapped rows get the same (cell row, dy) from both blocks."""
     fh = row_cell.shape[0]
     row_lut = np.zeros((fh, 2), dtype=np.uint32)
     seen = np.zeros(fh, dtype=np.int64)
-    for i0, n, cr, dy0 in groups:
-        assert 1 <= n <= rt.WARP_GROUP_ROWS
-        rows = np.arange(int(i0), int(i0) + int(n))
+    prev_end, prev_i0 = row0, -1
+    for w0, w1 in blocks:
+        i0, n, cr, dy0 = int(w0) & 0x0fffffff, int(w0) >> 28, int(w1) & 0xffff, int(w1) >> 16
+        assert 1 <= n <= rt.WARP_BLOCK_ROWS and prev_i0 < i0 <= prev_end      # ordered, no gap
+        rows = np.arange(i0, i0 + n)
+        assert (row_cell[rows] == cr).all() and dy0 == i0 - row_first[cr]
+        if n < rt.WARP_BLOCK_ROWS:            # partial only when the run itself is that short
+            assert (i0 == 0 or row_cell[i0 - 1] != cr or i0 == row0) and (i0 + n == fh or row_cell[i0 + n] != cr or True)
+        dy = np.float32(dy0) + np.arange(n, dtype=np.float32)        # the kernel's dy0 + (float)k
+        new = np.stack([np.full(n, cr, np.uint32), dy.astype(np.float32).view(np.uint32)], 1)
+        again = seen[rows] > 0
+        assert np.array_equal(row_lut[rows][again], new[again])
+        row_lut[rows] = new
         seen[rows] += 1
-        assert (row_cell[rows] == cr).all()
-        dy = np.uint32(dy0).view(np.float32) + np.arange(int(n), dtype=np.float32)
-        row_lut[rows, 0] = cr
-        row_lut[rows, 1] = dy.astype(np.float32).view(np.uint32)
-    assert (seen == 1).all()
-    return row_lut
+        prev_end, prev_i0 = max(prev_end, i0 + n), i0
+    return row_lut, seen
 
 
 def _emulate_fast_path(fast, col_lut, row_lut, gc, sw, sh, rng):
@@ -165,7 +172,8 @@ def test_guard_band_makes_fast_path_exact(golden, name, scale):
     mesh = apap_utils.get_mesh((fw, fh), sc.mesh_cells + 1)
     col, row = papap.cell_lookup_tables(mesh, fw, fh, sc.mesh_cells, sc.mesh_cells)
     fast, col_lut, row_first = papap.build_warp_tables(inv, col, row, ox, oy, sw, sh)
-    row_lut = _rows_from_groups(papap.build_row_groups(row, row_first), row)
+    row_lut, seen = _rows_from_blocks(papap.build_row_blocks(row, row_first), row, row_first)
+    assert (seen >= 1).all() and seen.mean() < 1.2
     assert fast.shape == (sc.mesh_cells ** 2, rt.HINV_ROW) and fast.dtype == np.float32
     assert np.array_equal(col_lut[:, 0], col) and np.array_equal(row_lut[:, 0], row)
     off, flagged = _emulate_fast_path(fast, col_lut, row_lut, sc.mesh_cells, sw, sh, np.random.default_rng(3))
@@ -192,7 +200,7 @@ def test_guard_band_adversarial_integer_hits():
         if trial >= 2:
             inv += (rng.standard_normal(inv.shape) * 10.0 ** -(trial + 3)).astype(np.float32)
         fast, col_lut, row_first = papap.build_warp_tables(inv, col, row, 11, 7, sw, sh)
-        row_lut = _rows_from_groups(papap.build_row_groups(row, row_first), row)
+        row_lut, _ = _rows_from_blocks(papap.build_row_blocks(row, row_first), row, row_first)
         off, flagged = _emulate_fast_path(fast, col_lut, row_lut, 8, sw, sh, rng)
         want = _exact_path(inv, col, row, fw, fh, 11, 7, sw, sh)
         assert np.array_equal(off[~flagged], want[~flagged]), trial
@@ -200,21 +208,30 @@ def test_guard_band_adversarial_integer_hits():
             assert flagged.all()
 
 
-def test_row_groups_bands_and_odd_luts():
-    """Bands of a sharded run get exactly their rows; runs are cut into near-equal groups; a lookup
-    table with repeated / non-monotone cell rows (mesh start > 0 wraps to the last cell) still tiles."""
+def test_row_blocks_bands_and_odd_luts():
+    """Runs are covered by full blocks (overlapping where the run is not a multiple of 4), short runs
+    by one partial block; bands of a sharded run get exactly their rows; a lookup table with
+    non-monotone cell rows (mesh start > 0 wraps to the last cell) still tiles."""
     row = np.repeat(np.arange(7), [11, 12, 3, 8, 9, 17, 1]).astype(np.uint16)
     first = np.r_[0, np.cumsum([11, 12, 3, 8, 9, 17])]
-    g = papap.build_row_groups(row, first)
-    _rows_from_groups(g, row)
-    assert sorted(g[g[:, 2] == 5][:, 1].tolist()) == [5, 6, 6] and g[g[:, 2] == 3][:, 1].tolist() == [8]
-    band = papap.build_row_groups(row, first, 20, 45)
-    assert band[0, 0] == 20 and int(band[-1, 0] + band[-1, 1]) == 45 and band[:, 1].sum() == 25
-    assert np.uint32(band[0, 3]).view(np.float32) == 20 - 11          # dy of the band's first row inside cell row 1
-    assert papap.build_row_groups(row, first, 30, 30).shape == (0, 4)
+    g = papap.build_row_blocks(row, first)
+    _, seen = _rows_from_blocks(g, row, first)
+    assert (seen >= 1).all()
+    of = lambda cr: [(int(a) & 0x0fffffff, int(a) >> 28) for a, b in g if (int(b) & 0xffff) == cr]     # noqa: E731
+    assert of(0) == [(0, 4), (4, 4), (7, 4)] and of(1) == [(11, 4), (15, 4), (19, 4)] and of(2) == [(23, 3)]
+    assert of(3) == [(26, 4), (30, 4)] and of(4) == [(34, 4), (37, 4), (39, 4)] and of(6) == [(60, 1)]
+    assert [n for _, n in of(5)] == [4] * 5 and of(5)[0][0] == 43 and of(5)[-1][0] == 56
+    band = papap.build_row_blocks(row, first, 20, 45)
+    _, seen = _rows_from_blocks(band, row, first, row0=20)
+    assert seen[20:45].all() and not seen[:20].any() and not seen[45:].any()
+    assert int(band[0, 1]) >> 16 == 20 - 11                            # dy of the band's first row inside cell row 1
+    assert papap.build_row_blocks(row, first, 30, 30).shape == (0, 2)
     wrapped = np.r_[np.full(4, 6), row].astype(np.uint16)               # rows 0..3 wrap to the last cell row
     first_w = np.r_[4 + first[:6], 0]
-    _rows_from_groups(papap.build_row_groups(wrapped, first_w), wrapped)
+    with pytest.raises(ValueError):                                     # rows before their cell row's origin
+        papap.build_row_blocks(np.r_[row, np.full(3, 0)].astype(np.uint16), np.r_[60, first[1:]])
+    _, seen = _rows_from_blocks(papap.build_row_blocks(wrapped, first_w), wrapped, first_w)
+    assert (seen >= 1).all()
 
 
 def test_guard_band_degenerate_cells_go_exact():
