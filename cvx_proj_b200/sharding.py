@@ -113,7 +113,8 @@ class ShardedAPAP:
 
         st, s = self.stitcher, self.me
         torch, device = rt.torch_cuda(st.device)
-        local_h_rows[...] = np.linalg.inv(local_h_rows)
+        from .apap import invert_grid_inplace
+        invert_grid_inplace(local_h_rows)
         full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
         full[...] = np.eye(3, dtype=np.float32)
         full[s.cell_row0:s.cell_row1] = local_h_rows
