@@ -202,20 +202,22 @@ class Timer:
 class Pass:
     """Device-resident state of one APAP pass (inputs already in HBM) + launch helpers."""
 
-    def __init__(self, torch, device, name, seed=0, rows=None):
+    def __init__(self, torch, device, name, seed=0, rows=None, gram_engine="tcgen05"):
         from cvx_proj_b200 import synth
         from cvx_proj_b200 import _runtime as rt
         from cvx_proj_b200.apap import APAP, cell_lookup_tables, scale_anchors, weight_scale
         self.torch, self.device, self.rt = torch, device, rt
         self.sc = sc = synth.make_scene(name, seed=seed)
-        self.st = APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y], device=device)
+        self.st = APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y], device=device,
+                       gram_engine=gram_engine)
         self.lib = rt.load_library()
         m = sc.mesh_cells
         self.row0, self.row1 = rows if rows is not None else (0, m)          # owned cell rows
         verts = sc.vertices[self.row0:self.row1]
         self.cells = verts.shape[0] * verts.shape[1]
         table, tmats = self.st._prepare(sc.src, sc.dst)
-        self.n_pad = table.shape[0]
+        self.engine = rt.GRAM_TCGEN05 if self.st.gram_engine == "tcgen05" else rt.GRAM_FFMA2
+        self.n_pad = table.shape[0] * (rt.KP_BLOCK if self.engine == rt.GRAM_TCGEN05 else 1)
         self.table = torch.from_numpy(table).to(device)
         self.anchors = torch.from_numpy(scale_anchors(verts, weight_scale(sc.sigma))).to(device)
         self.tmats = torch.from_numpy(tmats).to(device)
@@ -229,7 +231,7 @@ class Pass:
     # -- moving DLT
     def gram(self):
         self.rt.check(self.lib.apap_gram_partials(self.table.data_ptr(), self.anchors.data_ptr(), 1, self.cells,
-                                                  self.n_pad, self.g2, self.partials.data_ptr(),
+                                                  self.n_pad, self.g2, self.engine, self.partials.data_ptr(),
                                                   self.stream), "gram")
 
     def eig(self):

@@ -18,7 +18,11 @@ KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
 WARP_BLOCK_ROWS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
+KP_BLOCK = 8
+KP_BLOCK_FLOATS = 528
+GRAM_TCGEN05 = 0
+GRAM_FFMA2 = 1
 EIG_AUTO = 0
 EIG_JACOBI = 1
 
@@ -28,9 +32,9 @@ SIGNATURES = {
     "apap_last_error": (c_char_p, []),
     "apap_device_sm_count": (c_int, [POINTER(c_int)]),
     "apap_gram_plan": (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
-    "apap_gram_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "apap_gram_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "apap_eig_denorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+    "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "apap_local_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -27,9 +27,9 @@ from typing import NamedTuple
 import numpy as np
 
 from . import _runtime as rt
-from ._runtime import GRAM_TERMS, HINV_ROW, KP_CHUNK, KP_ROW, WARP_BLOCK_ROWS
+from ._runtime import GRAM_TERMS, HINV_ROW, KP_BLOCK, KP_BLOCK_FLOATS, KP_CHUNK, KP_ROW, WARP_BLOCK_ROWS
 
-__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "build_row_blocks", "cell_lookup_tables"]
+__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "build_kp_blocks", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "build_row_blocks", "cell_lookup_tables"]
 
 _U = 2.0 ** -24          # float32 unit roundoff
 
@@ -70,6 +70,32 @@ def build_kp_table(src_point: np.ndarray, dlt: np.ndarray, scale: float) -> np.n
     tab[:n, 24:26] = scaled[:, 0:1]
     tab[:n, 26:28] = scaled[:, 1:2]
     return tab
+
+
+def build_kp_blocks(table: np.ndarray) -> np.ndarray:
+    """Keypoint table of the tensor-core Gram kernel from the row table of ``build_kp_table``:
+    ``[N_padded / 8, 528]`` float32, one block per 8 keypoints = one K step of the TF32 MMA.
+
+    Block layout: the 8 x 64 tile ``[Ph | Pl]`` (512 floats), then ``s kx[8], s ky[8]``.
+    ``P = Ph + Pl`` exactly, ``Ph`` = P rounded to TF32 (10 mantissa bits, ties away -- the rounding of
+    ``cvt.rna.tf32.f32``); the kernel computes ``w_hi [Ph | Pl] + w_lo Ph`` (3xTF32).  ``P`` is the
+    8 x 32 matrix (keypoint k, term n; terms 24..31 are zero padding up to the MMA's N); the tile is
+    stored in the K-major core-matrix layout of the MMA's shared-memory descriptor: element
+    (k, column m) at float ``(k // 4) * 256 + (m // 8) * 32 + (m % 8) * 4 + k % 4``, ``m = n`` for
+    ``Ph`` and ``32 + n`` for ``Pl``."""
+    n_pad = table.shape[0]
+    n_kb = n_pad // KP_BLOCK
+    p = np.zeros((n_kb, KP_BLOCK, 32), dtype=np.float32)
+    p[:, :, :GRAM_TERMS] = table[:, :GRAM_TERMS].reshape(n_kb, KP_BLOCK, GRAM_TERMS)
+    hi = ((p.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = p - hi                                                       # exact in float32
+    tile = np.concatenate([hi, lo], axis=2)                           # [kb, k, m = 64]
+    out = np.empty((n_kb, KP_BLOCK_FLOATS), dtype=np.float32)
+    # [kb, k = (j, kk), m = (r1, r0)] -> [kb, j, r1, r0, kk]
+    out[:, :512] = tile.reshape(n_kb, 2, 4, 8, 8).transpose(0, 1, 3, 4, 2).reshape(n_kb, 512)
+    out[:, 512:520] = table[:, 24].reshape(n_kb, KP_BLOCK)
+    out[:, 520:528] = table[:, 26].reshape(n_kb, KP_BLOCK)
+    return out
 
 
 def scale_anchors(vertices, scale: float) -> np.ndarray:
@@ -395,9 +421,14 @@ class LazyLocalWeight:
 class APAP:
     """Drop-in for the reference ``APAP`` (pyviz/apap.py:21-217)."""
 
-    def __init__(self, gamma, sigma, final_size, offset, device=None):
+    def __init__(self, gamma, sigma, final_size, offset, device=None, gram_engine="tcgen05"):
         """``final_size = [width, height]`` of the stitched canvas, ``offset = [off_x, off_y]``
-        (pyviz/apap.py:22-32).  ``device`` (extension) selects the CUDA device."""
+        (pyviz/apap.py:22-32).  Extensions: ``device`` selects the CUDA device; ``gram_engine`` the
+        kernel of the moving-DLT contraction, ``"tcgen05"`` (tensor cores, 3xTF32, default) or
+        ``"ffma2"`` (FP32 SIMT)."""
+        if gram_engine not in ("tcgen05", "ffma2"):
+            raise ValueError("gram_engine must be 'tcgen05' or 'ffma2'")
+        self.gram_engine = gram_engine
         self.gamma = gamma
         self.sigma = sigma
         self.final_width, self.final_height = final_size
@@ -485,6 +516,8 @@ class APAP:
         cf2 = self.point_normalize(nf2, c2)
         dlt = self.matrix_generate(sample_n, cf1, cf2)
         table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
+        if self.gram_engine == "tcgen05":
+            table = build_kp_blocks(table)
         # h -> inv(N2) (inv(C2) h C1) N1   (pyviz/apap.py:165-166); inverses in float32 like the reference
         t2inv = np.linalg.inv(n2).astype(np.float64) @ np.linalg.inv(c2).astype(np.float64)
         t1 = c1.astype(np.float64) @ n1.astype(np.float64)
@@ -505,10 +538,12 @@ class APAP:
     def local_homography_device(self, table_dev, anchors_dev, tmats_dev, batch, cells, out_h=None, partials=None,
                                 sweeps=None, solver=rt.EIG_AUTO):
         """Device-resident K1 + K2 (no host traffic): tensors in, ``[batch, cells, 9]`` float32 out.
-        ``table_dev`` / ``anchors_dev`` hold pre-scaled coordinates (``build_kp_table``, ``scale_anchors``)."""
+        ``table_dev`` / ``anchors_dev`` hold pre-scaled coordinates (``build_kp_table`` or, for the
+        tensor-core engine, ``build_kp_blocks``; ``scale_anchors``); the engine follows from the table's shape."""
         torch, device = rt.torch_cuda(table_dev.device)
         lib = rt.load_library()
-        n_pad = table_dev.shape[-2]
+        engine = rt.GRAM_TCGEN05 if table_dev.shape[-1] == KP_BLOCK_FLOATS else rt.GRAM_FFMA2
+        n_pad = table_dev.shape[-2] * (KP_BLOCK if engine == rt.GRAM_TCGEN05 else 1)
         _, _, nbytes = rt.gram_plan(cells, n_pad)
         if partials is None:
             partials = torch.empty(batch * nbytes // 4, dtype=torch.float32, device=device)
@@ -517,7 +552,7 @@ class APAP:
         with torch.cuda.device(device):
             rt.check(lib.apap_local_homography(
                 table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
-                float(np.float32(float(self.gamma) ** 2)), int(solver), partials.data_ptr(), out_h.data_ptr(),
+                float(np.float32(float(self.gamma) ** 2)), engine, int(solver), partials.data_ptr(), out_h.data_ptr(),
                 sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
                 "apap_local_homography")
         return out_h
@@ -551,7 +586,7 @@ class APAP:
         cells = mesh_n * pt_size
         prepared = [self._prepare(s, d) for s, d in zip(src_points, dst_points)]
         n_pad = max(t.shape[0] for t, _ in prepared)
-        tables = np.zeros((count, n_pad, KP_ROW), dtype=np.float32)
+        tables = np.zeros((count, n_pad, prepared[0][0].shape[1]), dtype=np.float32)
         for k, (t, _) in enumerate(prepared):
             tables[k, :t.shape[0]] = t
         tmats = np.stack([m for _, m in prepared])

@@ -58,10 +58,14 @@ int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
 }
 
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
-                       float gamma_sq, float *partials, void *stream) {
+                       float gamma_sq, int engine, float *partials, void *stream) {
   int rc = check_table(kp_table, anchors, batch, cells, n_kp_padded);
   if (rc) return rc;
   if (!partials) return fail(APAP_E_BADARG, "null partials");
+  if (engine == APAP_GRAM_TCGEN05)
+    return launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials,
+                          static_cast<cudaStream_t>(stream));
+  if (engine != APAP_GRAM_FFMA2) return fail(APAP_E_BADARG, "gram: unknown engine");
   return launch_gram(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials,
                      static_cast<cudaStream_t>(stream));
 }
@@ -76,9 +80,9 @@ int apap_eig_denorm(const float *partials, const double *tmats, int batch, int c
 }
 
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats, int batch, int cells,
-                          int n_kp_padded, float gamma_sq, int solver,
+                          int n_kp_padded, float gamma_sq, int engine, int solver,
                           float *partials, float *out_h, int *out_sweeps, void *stream) {
-  int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials, stream);
+  int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, engine, partials, stream);
   if (rc) return rc;
   return apap_eig_denorm(partials, tmats, batch, cells, n_kp_padded, solver, out_h, out_sweeps, stream);
 }

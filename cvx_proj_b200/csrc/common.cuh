@@ -37,6 +37,8 @@ int check_cuda(cudaError_t e, const char *what);
 // launchers (one per translation unit)
 int launch_gram(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
                 float gamma_sq, float *partials, cudaStream_t st);
+int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded,
+                   float gamma_sq, float *partials, cudaStream_t st);
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded,
                float *out_h, int *out_sweeps, int force_jacobi, cudaStream_t st);
 int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,

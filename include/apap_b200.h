@@ -27,12 +27,14 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 2
+#define APAP_ABI_VERSION 3
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
 #define APAP_KP_ROW     28   /* floats per keypoint row: 24 product terms, s*kx (x2), s*ky (x2)   */
-#define APAP_KP_CHUNK   128  /* keypoint rows per shared-memory stage; tables are padded to this  */
+#define APAP_KP_CHUNK   128  /* keypoint tables are padded to a multiple of this many keypoints   */
+#define APAP_KP_BLOCK   8    /* keypoints per block of the tensor-core table (K of one TF32 MMA)  */
+#define APAP_KP_BLOCK_FLOATS 528 /* floats per block: [Ph | Pl] tile 512, s*kx[8], s*ky[8]           */
 #define APAP_HINV_ROW   12   /* floats per cell of the warp's fast-path record (see apap_warp)    */
 #define APAP_WARP_BLOCK_ROWS 4 /* most canvas rows per row block of the warp kernel               */
 
@@ -57,16 +59,26 @@ int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
 /*
  * K1 -- weights + Gram contraction.  Replaces, for every cell, pyviz/apap.py:150-152 (the
  * weight w_i = max(exp(-|v - x_i| / sigma^2), gamma)) and the row scaling + SVD input build of
- * pyviz/apap.py:159: it accumulates S_t(cell) = sum_i w_i^2 * kp_table[i][t] for the 24 terms.
+ * pyviz/apap.py:159: it accumulates S_t(cell) = sum_i w_i^2 * P[i][t] for the 24 product terms.
  * Coordinates arrive pre-scaled by s = 2 log2(e) / sigma^2, so w_i^2 = max(2^-|s v - s x_i|, gamma^2).
- *   kp_table : float [batch][n_kp_padded][APAP_KP_ROW]: 24 product terms, then s*kx, s*kx, s*ky,
- *              s*ky (the keypoint, each coordinate twice); rows past the real keypoints are zero
+ *   engine   : APAP_GRAM_TCGEN05 -- 3xTF32 tcgen05.mma, weights generated into tensor memory;
+ *              APAP_GRAM_FFMA2   -- FP32 SIMT (packed FFMA2)
+ *   kp_table : engine FFMA2:   float [batch][n_kp_padded][APAP_KP_ROW]: 24 product terms, then
+ *              s*kx, s*kx, s*ky, s*ky (the keypoint, each coordinate twice);
+ *              engine TCGEN05: float [batch][n_kp_padded / 8][APAP_KP_BLOCK_FLOATS]: per block of 8
+ *              keypoints the 8 x 64 tile [Ph | Pl] -- TF32 head and tail (P = Ph + Pl) of the 8 x 32
+ *              (24 terms + 8 zero columns) product matrix -- in the K-major core-matrix layout of the
+ *              MMA: element (keypoint k, column m) at float (k/4)*256 + (m/8)*32 + (m%8)*4 + k%4, m = n
+ *              for Ph, 32 + n for Pl; then s*kx[8], s*ky[8];
+ *              rows / blocks past the real keypoints are zero
  *   anchors  : float [batch][cells][2] = s * (x, y) of the cell anchor points (get_vertice)
- *   partials : float [batch][k_splits][24][cells_padded]
+ *   partials : float [batch][k_splits][24][cells_padded]  (same layout for both engines)
  *   gamma_sq = gamma^2
  */
+#define APAP_GRAM_TCGEN05 0
+#define APAP_GRAM_FFMA2   1
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells,
-                       int n_kp_padded, float gamma_sq, float *partials, void *stream);
+                       int n_kp_padded, float gamma_sq, int engine, float *partials, void *stream);
 
 /*
  * K2 -- per-cell 9x9 symmetric eigensolve + de-normalisation.  Replaces cv.SVDecomp + V[-1]
@@ -87,7 +99,7 @@ int apap_eig_denorm(const float *partials, const double *tmats, int batch, int c
 
 /* K1 + K2 back to back on `stream` (what APAP.local_homography calls). */
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats,
-                          int batch, int cells, int n_kp_padded, float gamma_sq, int solver,
+                          int batch, int cells, int n_kp_padded, float gamma_sq, int engine, int solver,
                           float *partials, float *out_h, int *out_sweeps, void *stream);
 
 /*

@@ -21,9 +21,12 @@ pytestmark = pytest.mark.gpu
 H_GATE = 1e-4
 
 
+ENGINES = ["tcgen05", "ffma2"]
+
+
 def _stitcher(sc, **kw):
     return APAP(kw.get("gamma", sc.gamma), kw.get("sigma", sc.sigma), [sc.final_w, sc.final_h],
-                [sc.offset_x, sc.offset_y])
+                [sc.offset_x, sc.offset_y], gram_engine=kw.get("engine", "tcgen05"))
 
 
 def _herr(h, ref, sc):
@@ -31,11 +34,12 @@ def _herr(h, ref, sc):
 
 
 # ------------------------------------------------------------------------------- moving DLT
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["tiny", "mini"])
-def test_local_homography_vs_reference_golden(golden, name):
+def test_local_homography_vs_reference_golden(golden, name, engine):
     g = golden(f"ref_{name}.npz")
     sc = synth.make_scene(name)
-    h, w = _stitcher(sc).local_homography(g["src"], g["dst"], g["vertices"])
+    h, w = _stitcher(sc, engine=engine).local_homography(g["src"], g["dst"], g["vertices"])
     assert h.shape == g["H"].shape and h.dtype == np.float32
     assert _herr(h, g["H"], sc).max() <= H_GATE
     assert w.shape == g["W"].shape
@@ -44,44 +48,50 @@ def test_local_homography_vs_reference_golden(golden, name):
     np.testing.assert_allclose(w[1], g["W"][1], rtol=1e-13, atol=0)
 
 
-def test_local_homography_c1_full_vs_reference(golden):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_local_homography_c1_full_vs_reference(golden, engine):
     g = golden("ref_c1.npz")
     sc = synth.make_scene("c1")
-    h, w = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+    h, w = _stitcher(sc, engine=engine).local_homography(sc.src, sc.dst, sc.vertices)
     err = _herr(h, g["H"], sc)
-    print(f"c1: normalised H error max {err.max():.3e}, raw elementwise {orc.h_error_raw(h, g['H']):.3e}")
+    print(f"c1 [{engine}]: normalised H error max {err.max():.3e}, raw elementwise {orc.h_error_raw(h, g['H']):.3e}")
     assert err.max() <= H_GATE
     np.testing.assert_allclose(np.asarray(w)[::9, ::9, ::7], g["W_sample"], rtol=1e-13, atol=0)
 
 
-def test_clamped_weights(golden):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_clamped_weights(golden, engine):
     g = golden("ref_tiny_sigma8.npz")
     sc = synth.make_scene("tiny")
-    h, w = _stitcher(sc, sigma=8.0).local_homography(sc.src, sc.dst, sc.vertices)
+    h, w = _stitcher(sc, sigma=8.0, engine=engine).local_homography(sc.src, sc.dst, sc.vertices)
     assert _herr(h, g["H"], sc).max() <= H_GATE
     wa = np.asarray(w)
     np.testing.assert_allclose(wa, g["W"], rtol=1e-13, atol=0)
     assert np.array_equal(wa == 0.5, g["W"] == 0.5)
 
 
-def test_c2_spot_cells_vs_reference_and_full_grid_vs_oracle(golden):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_c2_spot_cells_vs_reference_and_full_grid_vs_oracle(golden, engine):
     s = golden("ref_c2_spot.npz")
     sc = synth.make_scene("c2")
-    h, _ = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+    h, _ = _stitcher(sc, engine=engine).local_homography(sc.src, sc.dst, sc.vertices)
     got = h[s["rows"]][:, s["cols"]]
     err = _herr(got, s["H"], sc)
-    print(f"c2 spot: normalised H error max {err.max():.3e}, raw {orc.h_error_raw(got, s['H']):.3e}")
+    print(f"c2 spot [{engine}]: normalised H error max {err.max():.3e}, raw {orc.h_error_raw(got, s['H']):.3e}")
     assert err.max() <= H_GATE
     # every 5th row and column of the full grid against the float64 Gram oracle
     sub = sc.vertices[::5, ::5]
     ref = orc.local_homography_gram64(sc.src, sc.dst, sub, sc.gamma, sc.sigma)
-    assert _herr(h[::5, ::5], ref, sc).max() <= H_GATE
+    full = _herr(h[::5, ::5], ref, sc)
+    print(f"c2 grid [{engine}]: normalised H error vs float64 Gram oracle max {full.max():.3e} mean {full.mean():.3e}")
+    assert full.max() <= H_GATE
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("n_kp", [4, 7, 128, 129, 1500, 9000])
-def test_ragged_keypoint_counts(n_kp):
+def test_ragged_keypoint_counts(n_kp, engine):
     sc = synth.make_scene("mini", n_kp=n_kp, mesh=6)
-    h, _ = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+    h, _ = _stitcher(sc, engine=engine).local_homography(sc.src, sc.dst, sc.vertices)
     if n_kp >= 7:        # fewer than ~5 pairs leave the DLT rank-deficient; the reference's answer is arbitrary there
         ref = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
         assert _herr(h, ref, sc).max() <= H_GATE
@@ -115,24 +125,53 @@ def test_keypoint_permutation_invariance():
     assert _herr(h1, h0, sc).max() <= H_GATE
 
 
-def test_batch_equals_single_pairs_bitwise():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_batch_equals_single_pairs_bitwise(engine):
     scenes = [synth.make_scene("mini", seed=s, n_kp=n) for s, n in ((0, 200), (1, 333), (2, 120))]
-    st = _stitcher(scenes[0])
+    st = _stitcher(scenes[0], engine=engine)
     many = st.local_homography_batch([s.src for s in scenes], [s.dst for s in scenes], scenes[0].vertices)
     for sc, hb in zip(scenes, many):
         h1, _ = st.local_homography(sc.src, sc.dst, scenes[0].vertices)
         assert np.array_equal(hb, h1)
 
 
-def test_cell_row_sharding_is_bitwise_identical():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_cell_row_sharding_is_bitwise_identical(engine):
     """Rows solved on their own (what a rank of the multi-GPU run does) equal the same rows of the
-    full-grid solve bit for bit: the FP32 chain boundaries depend only on the keypoint count."""
+    full-grid solve bit for bit: the FP32 chain boundaries depend only on the keypoint count, and an
+    accumulator row of the tensor-core tile depends only on its own cell."""
     sc = synth.make_scene("c1", mesh=40)
-    st = _stitcher(sc)
+    st = _stitcher(sc, engine=engine)
     full, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
     for r0, r1 in sharding.split_rows(40, 3):
         part, _ = st.local_homography(sc.src, sc.dst, sc.vertices[r0:r1])
         assert np.array_equal(part, full[r0:r1])
+
+
+def test_gram_engines_agree_on_partial_sums():
+    """The tensor-core (3xTF32, TMEM) and the FP32 SIMT Gram kernels produce the same partial sums to
+    ~1e-6 of the largest sum of each term (tcgen05 accumulates per 256-keypoint segment)."""
+    import torch
+    from cvx_proj_b200.apap import build_kp_blocks, scale_anchors, weight_scale
+    sc = synth.make_scene("c1", mesh=37, n_kp=3001)
+    table, _ = _stitcher(sc, engine="ffma2")._prepare(sc.src, sc.dst)
+    lib = rt.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cells, n_pad = 37 * 37, table.shape[0]
+    ks, cp, nbytes = rt.gram_plan(cells, n_pad)
+    a = torch.from_numpy(scale_anchors(sc.vertices, weight_scale(sc.sigma))).to(dev)
+    out = {}
+    for engine, tab in ((rt.GRAM_FFMA2, table), (rt.GRAM_TCGEN05, build_kp_blocks(table))):
+        t = torch.from_numpy(tab).to(dev)
+        part = torch.zeros(nbytes // 4, dtype=torch.float32, device=dev)
+        rt.check(lib.apap_gram_partials(t.data_ptr(), a.data_ptr(), 1, cells, n_pad, 0.25, engine, part.data_ptr(),
+                                        rt.stream_ptr(torch, dev)), "gram")
+        out[engine] = part.cpu().numpy().reshape(ks, 24, cp)[:, :, :cells].astype(np.float64).sum(0)
+    ref, got = out[rt.GRAM_FFMA2], out[rt.GRAM_TCGEN05]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    err = np.abs(got - ref) / scale
+    print(f"gram engines: max |tcgen05 - ffma2| / max|sum| per term = {err.max():.3e}, mean {err.mean():.3e}")
+    assert err.max() <= 2e-5
 
 
 def test_eig_solvers_agree_and_report():

@@ -71,6 +71,32 @@ def test_kp_table_reproduces_weighted_gram(golden):
     assert np.array_equal(got, got.T)
 
 
+def test_kp_blocks_layout_and_split(golden):
+    """Tensor-core table: P = Ph + Pl exactly, Ph is TF32, element (k, n) sits where the MMA's K-major
+    core-matrix descriptor (LBO 512 B, SBO 128 B) expects it, coordinates follow."""
+    g = golden("ref_mini.npz")
+    tab = papap.build_kp_table(g["src"], g["A"], papap.weight_scale(100.0))
+    blk = papap.build_kp_blocks(tab)
+    n_kb = tab.shape[0] // rt.KP_BLOCK
+    assert blk.shape == (n_kb, rt.KP_BLOCK_FLOATS) and blk.dtype == np.float32
+    tile = blk[:, :512]
+    at = lambda k, m: (k // 4) * 256 + (m // 8) * 32 + (m % 8) * 4 + k % 4        # noqa: E731
+    hi_idx = [at(k, n) for k in range(8) for n in range(32)]
+    lo_idx = [at(k, 32 + n) for k in range(8) for n in range(32)]
+    assert sorted(hi_idx + lo_idx) == list(range(512))
+    assert not (tile[:, hi_idx].view(np.uint32) & 0x1FFF).any()        # TF32: low 13 mantissa bits clear
+    for kb, k, n in ((0, 0, 0), (3, 5, 17), (7, 7, 23), (11, 2, 8), (24, 4, 5)):
+        p = tab[kb * 8 + k, n]
+        h, l = tile[kb, at(k, n)], tile[kb, at(k, 32 + n)]
+        assert h + l == p and abs(l) <= abs(p) * 2.0 ** -11
+    # the 8 padding columns (terms 24..31) are zero in both halves
+    pad = [at(k, m) for k in range(8) for m in list(range(24, 32)) + list(range(56, 64))]
+    assert not tile[:, pad].any()
+    total = tile.astype(np.float64).sum()
+    assert total == tab[:, :24].astype(np.float64).sum()
+    assert np.array_equal(blk[:, 512:520].ravel(), tab[:, 24]) and np.array_equal(blk[:, 520:528].ravel(), tab[:, 26])
+
+
 def test_cell_lookup_matches_reference_rule(golden):
     g = golden("ref_mini.npz")
     fw, fh = int(g["final_size"][0]), int(g["final_size"][1])
@@ -267,7 +293,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 2
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 3
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stdint.h>
 
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
@@ -55,6 +56,17 @@ __global__ void __launch_bounds__(kThreads) probe(int iters, float seed, float *
     } else if (MODE == 9) {   // MUFU.RCP
 #pragma unroll
       for (int k = 0; k < kChains; ++k) { a[k].x = rcpa(a[k].x); a[k].y = rcpa(a[k].y); }
+    } else if (MODE == 11) {  // cvt.rna.tf32.f32
+#pragma unroll
+      for (int k = 0; k < kChains; ++k) {
+        uint32_t u, v;
+        asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a[k].x));
+        asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(v) : "f"(a[k].y));
+        a[k].x = __uint_as_float(u) + 1e-3f; a[k].y = __uint_as_float(v) + 1e-3f;
+      }
+    } else if (MODE == 12) {  // MUFU.SQRT + MUFU.EX2 + FMNMX chain (the weight)
+#pragma unroll
+      for (int k = 0; k < kChains; ++k) { a[k].x = fmaxf(ex2a(-sqa(a[k].x)), 0.25f) + 1.f; a[k].y = fmaxf(ex2a(-sqa(a[k].y)), 0.25f) + 1.f; }
     } else if (MODE == 10) {  // DFMA
       double *d = reinterpret_cast<double *>(a);
 #pragma unroll
@@ -281,6 +293,8 @@ int main() {
   run<9>("MUFU.RCP", 32, sms, ghz, sink);
   run<8>("FADD.RM (scalar)", 32, sms, ghz, sink);
   run<10>("DFMA", 16, sms, ghz, sink);
+  run<11>("cvt.rna.tf32.f32 (+FADD)", 32, sms, ghz, sink);
+  run<12>("weight: SQRT+EX2+FMNMX+FADD", 32, sms, ghz, sink);
   run<7>("gram mix (24 useful FMA)", 24, sms, ghz, sink);
   for (int w : {4, 12}) {
     run_pat<0>("tile: FFMA2 term-pairs, vector outer", w, sms, ghz, sink);
