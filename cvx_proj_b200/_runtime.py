@@ -40,7 +40,7 @@ SIGNATURES = {
     "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                           c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "apap_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "apap_fp32_probe": (c_int, [c_int, c_void_p, POINTER(c_double), c_void_p]),
+    "apap_pipe_probe": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
 }
 
 
@@ -161,22 +161,32 @@ def blend_host(img1, img2):
     return to_host(torch, blend_device(torch, a, b))
 
 
-def fp32_peak_tflops(device=None, iters: int = 1 << 16, reps: int = 5) -> float:
-    """Measured FP32 FMA-pipe peak (TFLOP/s): best of ``reps`` timed launches of the probe kernel."""
+PROBE_FFMA = 0
+PROBE_MUFU = 1
+
+
+def pipe_peak(kind: int, device=None, iters: int = 1 << 15, reps: int = 5) -> float:
+    """Measured peak of a pipe in operations/s (FFMA: flop/s, MUFU: lane-ops/s): best of ``reps``
+    timed launches of the probe kernel."""
     torch, device = torch_cuda(device)
     lib = load_library()
     sink = torch.zeros(1, dtype=torch.float32, device=device)
-    flops = c_double()
+    ops = c_double()
     best = 0.0
     with torch.cuda.device(device):
         st = stream_ptr(torch, device)
-        check(lib.apap_fp32_probe(iters, sink.data_ptr(), ctypes.byref(flops), st), "apap_fp32_probe")
+        check(lib.apap_pipe_probe(kind, iters, sink.data_ptr(), ctypes.byref(ops), st), "apap_pipe_probe")
         for _ in range(reps):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            check(lib.apap_fp32_probe(iters, sink.data_ptr(), ctypes.byref(flops), st), "apap_fp32_probe")
+            check(lib.apap_pipe_probe(kind, iters, sink.data_ptr(), ctypes.byref(ops), st), "apap_pipe_probe")
             e1.record()
             e1.synchronize()
-            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
     return best
+
+
+def fp32_peak_tflops(device=None) -> float:
+    """Measured FP32 FMA-pipe peak (TFLOP/s)."""
+    return pipe_peak(PROBE_FFMA, device, iters=1 << 16) / 1e12

@@ -112,9 +112,9 @@ int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, vo
   return launch_blend(a, b, out, n_px, static_cast<cudaStream_t>(stream));
 }
 
-int apap_fp32_probe(int iters, float *sink, double *flops, void *stream) {
+int apap_pipe_probe(int kind, int iters, float *sink, double *ops, void *stream) {
   if (!sink || iters <= 0) return fail(APAP_E_BADARG, "probe: bad arguments");
-  return launch_probe(iters, sink, flops, static_cast<cudaStream_t>(stream));
+  return launch_probe(kind, iters, sink, ops, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -48,7 +48,7 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
                 int off_x, int off_y, int row0, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
                 size_t out_band_bytes, int force_exact, cudaStream_t st);
 int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, cudaStream_t st);
-int launch_probe(int iters, float *sink, double *flops, cudaStream_t st);
+int launch_probe(int kind, int iters, float *sink, double *ops, cudaStream_t st);
 
 // ---- small PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -48,10 +48,32 @@ __global__ void __launch_bounds__(kProbeThreads) k_probe(int iters, float seed, 
   if (s == 123456.789f) *sink = s;   // never true; keeps the chains alive
 }
 
-int launch_probe(int iters, float *sink, double *flops, cudaStream_t st) {
+// 16 independent MUFU.EX2 chains per thread: the XU (special-function) pipe at saturation.
+__global__ void __launch_bounds__(kProbeThreads) k_probe_mufu(int iters, float seed, float *sink) {
+  float a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = seed - 1e-3f * (float)(threadIdx.x + k);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = ex2_approx(a[k]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 123456.789f) *sink = s;   // never true; keeps the chains alive
+}
+
+int launch_probe(int kind, int iters, float *sink, double *ops, cudaStream_t st) {
   const int blocks = sm_count_cached() * 8;
-  k_probe<<<blocks, kProbeThreads, 0, st>>>(iters, 0.f, sink);
-  if (flops) *flops = 2.0 * 16.0 * (double)iters * (double)blocks * kProbeThreads;
+  if (kind == APAP_PROBE_FFMA) {
+    k_probe<<<blocks, kProbeThreads, 0, st>>>(iters, 0.f, sink);
+    if (ops) *ops = 2.0 * 16.0 * (double)iters * (double)blocks * kProbeThreads;
+  } else if (kind == APAP_PROBE_MUFU) {
+    k_probe_mufu<<<blocks, kProbeThreads, 0, st>>>(iters, 0.f, sink);
+    if (ops) *ops = 16.0 * (double)iters * (double)blocks * kProbeThreads;
+  } else {
+    return fail(APAP_E_BADARG, "probe: unknown kind");
+  }
   return check_cuda(cudaGetLastError(), "k_probe launch");
 }
 

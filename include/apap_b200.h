@@ -150,11 +150,17 @@ int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, 
 int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream);
 
 /*
- * FP32 FMA-pipe probe: runs `iters` x 16 dependent-chain-free FFMAs per thread on every SM and
- * returns the flop count; the caller times it with events to get the measured FP32 peak that the
- * Gram kernel's roofline fraction is quoted against.  sink: float [1] device scratch.
+ * Pipe probes for the roofline denominators that MEASURED_PEAKS.json does not hold.  Runs `iters` x 16
+ * independent operations per thread on every SM and returns the operation count in `ops`; the caller
+ * times the launch with events.
+ *   APAP_PROBE_FFMA : FP32 FMA pipe, ops = flop (2 per FFMA)   -> the FFMA2 Gram kernel's peak
+ *   APAP_PROBE_MUFU : XU pipe (MUFU.EX2), ops = lane operations -> the tcgen05 Gram kernel's peak
+ *                     (its weight generation costs 2 MUFU per cell-keypoint pair)
+ * sink: float [1] device scratch.
  */
-int apap_fp32_probe(int iters, float *sink, double *flops, void *stream);
+#define APAP_PROBE_FFMA 0
+#define APAP_PROBE_MUFU 1
+int apap_pipe_probe(int kind, int iters, float *sink, double *ops, void *stream);
 
 #ifdef __cplusplus
 }
