@@ -452,257 +452,6 @@ def run_ours(args):
                 "peak_source": "FP32 FFMA probe kernel timed in this run (not in MEASURED_PEAKS.json)",
                 "algorithmic": "2*24*n_kp_padded*cells flop per launch (24 executed terms)",
                 "ms": ms_gram, "eig_ms": ms_dlt - ms_gram}
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": _workload_desc(name)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
-
-
-def _workload_desc(name):
-    from cvx_proj_b200 import synth
-    c = synth.CONFIGS[name]
-    return (f"{name}: synthetic {c['width']}x{c['height']} pair, {c['n_kp']} matched keypoints, "
-            f"APAP {c['mesh']}x{c['mesh']} grid, gamma=0.5 sigma=100")
-
-
-# ----------------------------------------------------------------------------------- our arm
-class Timer:
-    def __init__(self, torch):
-        self.torch = torch
-        self.pairs = []
-
-    def mark(self):
-        e = self.torch.cuda.Event(enable_timing=True)
-        e.record()
-        return e
-
-    @staticmethod
-    def ms(a, b):
-        return a.elapsed_time(b)
-
-
-class Pass:
-    """Device-resident state of one APAP pass (inputs already in HBM) + launch helpers."""
-
-    def __init__(self, torch, device, name, seed=0, rows=None, gram_engine="tcgen05"):
-        from cvx_proj_b200 import synth
-        from cvx_proj_b200 import _runtime as rt
-        from cvx_proj_b200.apap import APAP, cell_lookup_tables, scale_anchors, weight_scale
-        self.torch, self.device, self.rt = torch, device, rt
-        self.sc = sc = synth.make_scene(name, seed=seed)
-        self.st = APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y], device=device,
-                       gram_engine=gram_engine)
-        self.lib = rt.load_library()
-        m = sc.mesh_cells
-        self.row0, self.row1 = rows if rows is not None else (0, m)          # owned cell rows
-        verts = sc.vertices[self.row0:self.row1]
-        self.cells = verts.shape[0] * verts.shape[1]
-        table, tmats = self.st._prepare(sc.src, sc.dst)
-        self.engine = rt.GRAM_TCGEN05 if self.st.gram_engine == "tcgen05" else rt.GRAM_FFMA2
-        self.n_pad = table.shape[0] * (rt.KP_BLOCK if self.engine == rt.GRAM_TCGEN05 else 1)
-        self.table = torch.from_numpy(table).to(device)
-        self.anchors = torch.from_numpy(scale_anchors(verts, weight_scale(sc.sigma))).to(device)
-        self.tmats = torch.from_numpy(tmats).to(device)
-        self.k_splits, self.cells_padded, nbytes = rt.gram_plan(self.cells, self.n_pad)
-        self.partials = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
-        self.h_out = torch.empty((self.cells, 9), dtype=torch.float32, device=device)
-        self.g2 = float(np.float32(float(sc.gamma) ** 2))
-        self.col_cell, self.row_cell = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, m, m)
-        self.stream = rt.stream_ptr(torch, device)
-
-    # -- moving DLT
-    def gram(self):
-        self.rt.check(self.lib.apap_gram_partials(self.table.data_ptr(), self.anchors.data_ptr(), 1, self.cells,
-                                                  self.n_pad, self.g2, self.engine, self.partials.data_ptr(),
-                                                  self.stream), "gram")
-
-    def eig(self):
-        self.rt.check(self.lib.apap_eig_denorm(self.partials.data_ptr(), self.tmats.data_ptr(), 1, self.cells,
-                                               self.n_pad, self.rt.EIG_AUTO, self.h_out.data_ptr(), None, self.stream),
-                      "eig")
-
-    # -- warp
-    def prepare_warp(self, px_rows=None):
-        """Upload the image, the inverted grid rows and the lookup tables (outside the timed region)."""
-        from cvx_proj_b200 import synth
-        torch, sc = self.torch, self.sc
-        self.torch.cuda.synchronize()
-        m = sc.mesh_cells
-        h = np.tile(np.eye(3, dtype=np.float32), (m, m, 1, 1))
-        h[self.row0:self.row1] = self.h_out.cpu().numpy().reshape(-1, m, 3, 3)
-        inv = np.linalg.inv(h).astype(np.float32)
-        img = sc.image(1)
-        centre = synth.make_image(sc.width, sc.height, seed=2)
-        self.px_rows = px_rows if px_rows is not None else (0, sc.final_h)
-        self.tables = self.st.warp_tables_device(inv, self.col_cell, self.row_cell, sc.width, sc.height, self.device,
-                                                 self.px_rows[0], self.px_rows[1])
-        self.flagged_cells = self.tables.exact_cells_frac
-        self.img = torch.from_numpy(img).to(self.device)
-        self.centre = torch.from_numpy(centre).to(self.device)
-        n = self.px_rows[1] - self.px_rows[0]
-        self.canvas = torch.empty((n, sc.final_w, 3), dtype=torch.uint8, device=self.device)
-        self.canvas2 = torch.empty_like(self.canvas)
-        self.pasted = torch.zeros_like(self.canvas)
-        self.host_img, self.host_centre = img, centre
-
-    def warp(self, fused=False):
-        self.st.warp_device(self.img, self.tables, self.sc.mesh_cells, centre_dev=self.centre if fused else None,
-                            out=self.canvas)
-
-    def blend(self):
-        self.rt.blend_device(self.torch, self.canvas, self.pasted, out=self.canvas2)
-
-
-def timed_steps(torch, flush, warmup, steps, body, n_marks):
-    """Run ``body(mark)`` warmup+steps times; ``body`` calls ``mark()`` n_marks times.  Returns the
-    per-interval mean milliseconds over the timed steps (list of n_marks-1 floats)."""
-    all_marks = []
-    for k in range(warmup + steps):
-        flush.add_(1)                       # 256 MiB write: evicts the 126 MB L2
-        marks = []
-        body(lambda: marks.append(_ev(torch)))
-        if k >= warmup:
-            all_marks.append(marks)
-    torch.cuda.synchronize()
-    sums = [0.0] * (n_marks - 1)
-    for marks in all_marks:
-        for i in range(n_marks - 1):
-            sums[i] += marks[i].elapsed_time(marks[i + 1])
-    return [s / steps for s in sums]
-
-
-def _ev(torch):
-    e = torch.cuda.Event(enable_timing=True)
-    e.record()
-    return e
-
-
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    from cvx_proj_b200 import _runtime as rt
-    from cvx_proj_b200 import sharding, synth
-
-    peaks, peak_src = _peaks()
-    name = args.workload or "c2"
-    K, W = args.steps, max(args.warmup, 3)
-    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=device)
-    launches = 0
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    fp32_peak = rt.fp32_peak_tflops(device)
-    mufu_peak = rt.pipe_peak(rt.PROBE_MUFU, device) / 1e12                    # Tlane-op/s
-    p = Pass(torch, device, name, seed=rank, gram_engine=args.gram_engine)
-    sc = p.sc
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-
-    # ---- stage 1: moving DLT (K1 + K2) ---------------------------------------------------------
-    def dlt_body(mark):
-        mark(); p.gram(); mark(); p.eig(); mark()
-    barrier()
-    t_gram, t_eig = timed_steps(torch, flush, W, K, dlt_body, 3)
-    barrier()
-    launches += 2 * K
-    ms_dlt = max_over_ranks(t_gram + t_eig)
-    ms_gram = max_over_ranks(t_gram)
-    cells_total = p.cells * world
-    value = cells_total / (ms_dlt * 1e-3)
-
-    # ---- stage 2: mesh warp (K3), blend (K4), fused K3+K4 -------------------------------------
-    p.prepare_warp()
-    barrier()
-    (t_warp,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(False), mark()), 2)
-    (t_fused,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(True), mark()), 2)
-    (t_blend,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.blend(), mark()), 2)
-    barrier()
-    launches += 3 * K
-    ms_warp, ms_fused, ms_blend = (max_over_ranks(t) for t in (t_warp, t_fused, t_blend))
-    canvas_px = sc.canvas_px
-    src_px = sc.width * sc.height
-    warp_bytes = 3 * canvas_px + 3 * src_px                       # SURVEY.md 8d: write canvas once + read source once
-    fused_bytes = 3 * canvas_px + 3 * src_px + 3 * src_px
-    blend_bytes = 9 * canvas_px
-    hbm = peaks["hbm_gbs"]
-
-    # ---- e2e through the public API: pinned host buffers in, host arrays out -------------------
-    src_pin = rt.pinned_empty(sc.src.shape, np.float32); src_pin[...] = sc.src
-    dst_pin = rt.pinned_empty(sc.dst.shape, np.float32); dst_pin[...] = sc.dst
-    img_pin = rt.pinned_empty(p.host_img.shape, np.uint8); img_pin[...] = p.host_img
-    st = p.st
-    e2e_dlt, e2e_warp = [], []
-    h_host = None
-    for k in range(W + K):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        h_host, _ = st.local_homography(src_pin, dst_pin, sc.vertices)
-        t1 = time.perf_counter()
-        warped = st.local_warp(img_pin, h_host, sc.mesh)
-        t2 = time.perf_counter()
-        if k >= W:
-            e2e_dlt.append(t1 - t0)
-            e2e_warp.append(t2 - t1)
-    launches += 3 * K
-    e2e_dlt_s = max_over_ranks(float(np.mean(e2e_dlt)))
-    e2e_warp_s = max_over_ranks(float(np.mean(e2e_warp)))
-    h2d_dlt = p.n_pad * 28 * 4 + p.cells * 8 + 144
-    d2h_dlt = p.cells * 36
-    h2d_warp = 3 * src_px + p.cells * 48 + 2 * (sc.final_w + sc.final_h)
-    d2h_warp = 3 * canvas_px
-
-    # ---- c3 strong-scaled across ranks (cell rows + row bands, one all-gather) -----------------
-    c3 = None
-    if args.c3 and (world > 1 or args.c3 == "always"):
-        c3 = run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks, barrier)
-        launches += c3.pop("_launches")
-
-    clocks = sampler.stop() if rank == 0 else None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- CPU baseline (rank 0, N = 1 only): bounded samples of the same workload ---------------
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        procs = os.cpu_count() or 1
-        n_cells = int(min(sc.n_cells, max(4 * procs, 12.0 / (2.5e-3 * sc.src.shape[0] / 5000 + 3e-4))))
-        rate, wall = cpu_moving_dlt(name, n_cells, procs)
-        wrate, wwall = cpu_warp(name, 256)
-        cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": (f"{n_cells} of {sc.n_cells} cells of {name} (evenly spread), oracle per-cell weighted SVD "
-                          f"(cv.SVDecomp float64, the reference's algorithm) over {procs} processes, {wall:.1f} s wall"),
-               "warp": {"value": wrate, "unit": "Mpix/s", "cores": 1,
-                        "sample": f"first 256 canvas rows of {name}, oracle vectorised float64 numpy, {wwall:.1f} s"}}
-
-    gram_flops = 2.0 * 24 * p.n_pad * p.cells
-    achieved_tf = gram_flops / (ms_gram * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dlt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -720,7 +469,7 @@ def run_ours(args):
             "ms_per_step": ms_warp, "dtype": "u8",
             "roofline": {"kernel": "k_warp", "bound": "hbm", "achieved": warp_bytes / (ms_warp * 1e-3) / 1e9,
                          "peak": hbm, "unit": "GB/s", "frac": warp_bytes / (ms_warp * 1e-3) / 1e9 / hbm,
-                         "traffic": traffic.get("k_warp"), "peak_source": peak_src,
+                         "traffic": traffic.get("k_warp<0, 1>"), "peak_source": peak_src,
                          "algorithmic": "3*canvas_px + 3*src_px bytes per launch"},
             "fused_warp_blend": {"ms_per_step": ms_fused, "mpix_per_s": canvas_px / (ms_fused * 1e-3) / 1e6,
                                  "hbm_frac": fused_bytes / (ms_fused * 1e-3) / 1e9 / hbm},

@@ -31,7 +31,7 @@ KEEP = [
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe %"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
-    ("SM_A.TriageCompute.sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed", "XU pipe %"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe %"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
@@ -72,7 +72,7 @@ def main():
         tot = sum(v for _, v in stalls) or 1.0
         top = ", ".join(f"{h} {100 * v / tot:.0f}%" for h, v in sorted(stalls, key=lambda x: -x[1])[:5])
         out.append(f"| top stall reasons (sampled) | {top} |\n")
-        traffic[re.sub(r"<.*", "", name)] = int(dram)
+        traffic[name] = int(dram)
     os.makedirs(os.path.join(REPO, "profiles"), exist_ok=True)
     md = os.path.join(REPO, "profiles", f"{rnd}_ncu_summary.md")
     with open(md, "w") as f:
