@@ -11,7 +11,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_void
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libapap_b200.so")
+# APAP_B200_LIB: lab builds of the same library (tools/variants.sh); the product is the in-tree file
+LIB_PATH = os.environ.get("APAP_B200_LIB") or os.path.join(_HERE, "libapap_b200.so")
 
 GRAM_TERMS = 24
 KP_ROW = 28

@@ -17,7 +17,10 @@ constexpr int kHinvRow = APAP_HINV_ROW;     // 12 floats = 48 B per cell
 // Longest FP32 accumulation chain the Gram kernel runs before its sum leaves the register
 // (SURVEY.md finding 8: <= 1024 sequential FP32 terms, then a float64 combine, keeps the
 // per-cell H inside the 1e-4 gate; a single chain over all N does not).
-constexpr int kMaxChainChunks = 8;          // 8 x 128 = 1024 keypoints per split
+#ifndef APAP_MAX_CHAIN_CHUNKS
+#define APAP_MAX_CHAIN_CHUNKS 8
+#endif
+constexpr int kMaxChainChunks = APAP_MAX_CHAIN_CHUNKS;   // 8 x 128 = 1024 keypoints per split
 
 struct GramPlan {
   int k_splits;
