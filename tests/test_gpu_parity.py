@@ -98,6 +98,19 @@ def test_ragged_keypoint_counts(n_kp, engine):
     assert np.isfinite(h).all() or n_kp < 7
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("gamma,sigma", [(0.5, 100), (0.3, 100), (0.8, 100), (0.05, 20), (0.5, 8), (0.9999, 100)])
+def test_clamp_and_falloff_sweep(gamma, sigma, engine):
+    """gamma decides which weight path the tensor-core kernel takes (polynomial 2^-t for gamma >= 0.5,
+    MUFU.EX2 below); sigma moves the weights between ~1 everywhere and clamped almost everywhere."""
+    sc = synth.make_scene("mini", n_kp=700, mesh=12)
+    h, _ = _stitcher(sc, engine=engine, gamma=gamma, sigma=sigma).local_homography(sc.src, sc.dst, sc.vertices)
+    ref = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, gamma, sigma)
+    err = _herr(h, ref, sc)
+    print(f"gamma {gamma} sigma {sigma} [{engine}]: normalised H error max {err.max():.3e}")
+    assert err.max() <= H_GATE
+
+
 def test_exact_homography_gives_global_h_everywhere():
     sc = synth.make_scene("mini", n_kp=400)
     hom = np.concatenate([sc.src.astype(np.float64), np.ones((400, 1))], 1) @ sc.h_gt.T

@@ -1,1 +1,3 @@
-APAP_B200_LIB=cvx_proj_b200/lab/trace.so python tools/gram_scan.py 3776:5120 | head -50
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 120 python tools/time_kernels.py c2 10 gram,eig
+timeout 120 python tools/time_kernels.py c3 5 gram,eig

@@ -64,25 +64,19 @@ try:
     print("  resident CTAs at t = 0, 5, 10 ... us:", conc)
 except AttributeError:
     pass
-if hasattr(lib, "apap_lab_trace") or True:
-    import ctypes
-    try:
-        fn = lib.apap_lab_trace
-    except AttributeError:
-        fn = None
-    if fn is not None:
-        buf = np.zeros((4, 160, 4), dtype=np.int64)
-        fn.argtypes = [ctypes.c_void_p]
-        fn(buf.ctypes.data)
-        dc = buf[3, 151, 0] - buf[3, 150, 0]; dt = buf[3, 151, 1] - buf[3, 150, 1]
-        print(f"TMA thread first -> last stage: {dc} SM cycles in {dt} ns = {dc / max(dt, 1):.3f} GHz")
-        buf[3, 150:] = 0
-        t0 = buf[buf > 0].min()
-        rel = np.where(buf > 0, buf - t0, -1)
-        print("trace of the last launch, CTA x=TRACE id, split 0 (SM clock cycles since first mark)")
-        print("producer warp 0: step: before-wait a_empty | after | before wait::st | after arrive     (warp 3 in brackets)")
-        for s_ in range(0, 70):
-            if rel[0, s_, 0] < 0:
-                break
-            print(f"  P step {s_:3d}: " + " ".join(f"{v:7d}" for v in rel[0, s_]) + "   [" + " ".join(f"{v:7d}" for v in rel[3, s_]) + "]"
-                  + f"   MMA: {rel[1, s_, 0]:7d} {rel[1, s_, 1]:7d} {rel[1, s_, 2]:7d}" + (f"   TMA st {s_}: {rel[2, s_, 0]:7d} {rel[2, s_, 1]:7d}" if rel[2, s_, 0] >= 0 else ""))
+try:
+    fn = lib.apap_lab_trace
+    fn.argtypes = [ctypes.c_void_p]
+    buf = np.zeros((4, 160, 4), dtype=np.int64)
+    fn(buf.ctypes.data)
+    t0 = buf[buf > 0].min()
+    rel = np.where(buf > 0, buf - t0, -1)
+    print("trace of the last launch, CTA x = TRACE id, split 0 (SM clock cycles since the first mark)")
+    print("producer parity 0 | parity 1 (quarter 0): start, stage landed + probe issued, slot acquired, arrived;  MMA: wait, a_full seen, issued")
+    for it in range(0, 40):
+        if rel[0, it, 0] < 0:
+            break
+        print(f"  it {it:3d}: " + " ".join(f"{v:7d}" for v in rel[0, it]) + "  |" + " ".join(f"{v:7d}" for v in rel[1, it])
+              + f"   MMA step {2 * it}: " + " ".join(f"{v:7d}" for v in rel[2, 2 * it, :3]) + f"  step {2 * it + 1}: " + " ".join(f"{v:7d}" for v in rel[2, 2 * it + 1, :3]))
+except AttributeError:
+    pass
