@@ -9,7 +9,9 @@ missing.
 """
 from .apap_utils import final_size, get_mesh, get_vertice, uniform_blend
 
-__all__ = ["APAP", "final_size", "get_mesh", "get_vertice", "uniform_blend"]
+from .driver import mat_layout, save2mat, stitch_pair
+
+__all__ = ["APAP", "final_size", "get_mesh", "get_vertice", "uniform_blend", "mat_layout", "save2mat", "stitch_pair"]
 __version__ = "0.1.0"
 
 

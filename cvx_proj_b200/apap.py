@@ -29,7 +29,7 @@ import numpy as np
 from . import _runtime as rt
 from ._runtime import GRAM_TERMS, HINV_ROW, KP_BLOCK, KP_BLOCK_FLOATS, KP_CHUNK, KP_ROW, WARP_BLOCK_ROWS
 
-__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "build_kp_blocks", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "build_row_blocks", "cell_lookup_tables"]
+__all__ = ["APAP", "LazyLocalWeight", "build_kp_table", "build_kp_blocks", "scale_anchors", "weight_scale", "expand_gram", "build_warp_tables", "warp_luts", "build_row_blocks", "cell_lookup_tables"]
 
 _U = 2.0 ** -24          # float32 unit roundoff
 
@@ -73,7 +73,8 @@ def build_kp_table(src_point: np.ndarray, dlt: np.ndarray, scale: float) -> np.n
 
 
 def build_kp_blocks(table: np.ndarray) -> np.ndarray:
-    """Keypoint table of the tensor-core Gram kernel from the row table of ``build_kp_table``:
+    """Host restatement of ``apap_kp_blocks`` (the product packs the blocks on the device, same bits --
+    tests): keypoint table of the tensor-core Gram kernel from the row table of ``build_kp_table``:
     ``[N_padded / 8, 528]`` float32, one block per 8 keypoints = one K step of the TF32 MMA.
 
     Block layout: the 8 x 64 tile ``[Ph | Pl]`` (512 floats), then ``s kx[8], s ky[8]``.
@@ -178,9 +179,30 @@ def _cell_extent(lut: np.ndarray, n: int):
     return lo, hi
 
 
+def warp_luts(col_cell: np.ndarray, row_cell: np.ndarray, grid_rows: int, grid_cols: int):
+    """The O(canvas edge) lookup inputs of the warp: ``(col_lut[W, 2] u32, row_first[grid_rows] i64,
+    col_extent[grid_cols, 2] i32, row_extent[grid_rows, 2] i32)``.  ``col_lut[j] = (cell column, float32
+    bits of dx)``, ``dx = j - (first canvas column of that cell)``; an extent is the ``{first, last}`` canvas
+    column / row the reference's lookup (pyviz/apap.py:207,209) maps to the cell, ``first > last`` for
+    a cell no pixel maps to.  These feed ``apap_warp_tables`` (device) and ``build_row_blocks``."""
+    col64, row64 = col_cell.astype(np.int64), row_cell.astype(np.int64)
+    jlo, jhi = _cell_extent(col64, grid_cols)
+    ilo, ihi = _cell_extent(row64, grid_rows)
+    col_used, row_used = jlo <= jhi, ilo <= ihi
+    col_extent = np.stack([np.where(col_used, jlo, 1), np.where(col_used, jhi, 0)], axis=1).astype(np.int32)
+    row_extent = np.stack([np.where(row_used, ilo, 1), np.where(row_used, ihi, 0)], axis=1).astype(np.int32)
+    col_lut = np.empty((col_cell.shape[0], 2), dtype=np.uint32)
+    col_lut[:, 0] = col_cell
+    col_lut[:, 1] = (np.arange(col_cell.shape[0]) - np.where(col_used, jlo, 0)[col64]).astype(np.float32).view(np.uint32)
+    return col_lut, np.where(row_used, ilo, 0), col_extent, row_extent
+
+
 def build_warp_tables(inv_h: np.ndarray, col_cell: np.ndarray, row_cell: np.ndarray, off_x: int, off_y: int,
                       src_w: int, src_h: int):
     """Kernel inputs of the mesh warp: ``(cell_fast[cells, 12] f32, col_lut[W, 2] u32, row_first[grid_rows] i64)``.
+
+    Host restatement of the device kernel ``k_warp_prep`` (``apap_warp_tables``; the product path builds
+    the records there, bit-identical to this function -- tests); the CPU tests of the guard band run on it.
 
     ``col_lut[j] = (cell column, float32 bits of dx)`` with ``dx = j - (first canvas column of that
     cell)``; ``row_first[m]`` is the first canvas row of cell row m (``dy = i - row_first``, see
@@ -353,7 +375,11 @@ class WarpTables(NamedTuple):
     n_blocks: int
     row0: int               # the band of canvas rows the blocks cover
     row1: int
-    exact_cells_frac: float  # share of cells whose every pixel takes the float64 path
+
+    def exact_cells_frac(self) -> float:
+        """Share of cells whose every pixel takes the float64 path (reads the records back)."""
+        rec = self.cell_fast.view(-1, HINV_ROW)[:, 11]
+        return float((rec < 0).float().mean().item())
 
 
 class LazyLocalWeight:
@@ -504,7 +530,9 @@ class APAP:
     # ---- moving DLT ----------------------------------------------------------------------------
     def _prepare(self, src_point, dst_point):
         """Host prologue of ``local_homography`` (pyviz/apap.py:129-145): normalise, condition,
-        build the DLT matrix; then pack the kernel inputs."""
+        build the DLT matrix; then the keypoint ROW table (``build_kp_table``) and the two 3x3
+        de-normalisation matrices.  The tensor-core engine's block table is packed from the rows on the
+        device (``kp_table_device``)."""
         src_point = np.asarray(src_point)
         dst_point = np.asarray(dst_point)
         sample_n, _ = src_point.shape
@@ -516,8 +544,6 @@ class APAP:
         cf2 = self.point_normalize(nf2, c2)
         dlt = self.matrix_generate(sample_n, cf1, cf2)
         table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
-        if self.gram_engine == "tcgen05":
-            table = build_kp_blocks(table)
         # h -> inv(N2) (inv(C2) h C1) N1   (pyviz/apap.py:165-166); inverses in float32 like the reference
         t2inv = np.linalg.inv(n2).astype(np.float64) @ np.linalg.inv(c2).astype(np.float64)
         t1 = c1.astype(np.float64) @ n1.astype(np.float64)
@@ -534,6 +560,21 @@ class APAP:
         t_u8, a_u8, m_u8 = self._stage.upload(torch, device, (tables, anchors, tmats))
         return (t_u8.view(torch.float32).view(tables.shape), a_u8.view(torch.float32).view(anchors.shape),
                 m_u8.view(torch.float64).view(tmats.shape))
+
+    def kp_table_device(self, rows_dev):
+        """Device keypoint table of this instance's Gram engine from the uploaded row table
+        ``[batch, n_pad, 28]``: the rows themselves (``ffma2``) or the block table ``[batch, n_pad / 8, 528]``
+        packed by ``apap_kp_blocks`` (``tcgen05``; same bits as ``build_kp_blocks``)."""
+        if self.gram_engine != "tcgen05":
+            return rows_dev
+        torch, device = rt.torch_cuda(rows_dev.device)
+        lib = rt.load_library()
+        batch, n_pad, _ = rows_dev.shape
+        blocks = torch.empty((batch, n_pad // KP_BLOCK, KP_BLOCK_FLOATS), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_kp_blocks(rows_dev.data_ptr(), batch, n_pad, blocks.data_ptr(),
+                                        rt.stream_ptr(torch, device)), "apap_kp_blocks")
+        return blocks
 
     def local_homography_device(self, table_dev, anchors_dev, tmats_dev, batch, cells, out_h=None, partials=None,
                                 sweeps=None, solver=rt.EIG_AUTO):
@@ -571,7 +612,7 @@ class APAP:
         cells = mesh_n * pt_size
         anchors = scale_anchors(vertices, weight_scale(self.sigma))
         t_dev, a_dev, m_dev = self._upload_scene(torch, device, table[None], anchors[None], tmats[None])
-        h_dev = self.local_homography_device(t_dev, a_dev, m_dev, 1, cells)
+        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, 1, cells)
         h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
         weight = LazyLocalWeight(np.asarray(src_point), np.asarray(vertices), self.gamma, self.sigma, self.device)
         return h, weight
@@ -593,7 +634,7 @@ class APAP:
         anchors = np.stack([scale_anchors(v, weight_scale(self.sigma)) for v in verts])
         torch, device = rt.torch_cuda(self.device)
         t_dev, a_dev, m_dev = self._upload_scene(torch, device, tables, anchors, tmats)
-        h_dev = self.local_homography_device(t_dev, a_dev, m_dev, count, cells)
+        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, count, cells)
         h = rt.to_host(torch, h_dev).reshape(count, mesh_n, pt_size, 3, 3)
         return [h[k] for k in range(count)]
 
@@ -608,20 +649,33 @@ class APAP:
         return hit
 
     def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None, row0=0, row1=None):
-        """Build the warp kernel's tables (``build_warp_tables`` + ``build_row_blocks`` for the canvas
-        rows ``[row0, row1)``) for an inverted grid and upload them with one host->device copy."""
+        """The warp kernel's inputs for an inverted grid and the canvas rows ``[row0, row1)``: one
+        host->device copy (inverted grid, column LUT, row blocks, cell extents), then the per-cell
+        fast-path records are built on the device (``apap_warp_tables``)."""
         torch, device = rt.torch_cuda(device if device is not None else self.device)
+        lib = rt.load_library()
         row1 = int(self.final_height) if row1 is None else row1
-        fast, col_lut, row_first = build_warp_tables(inv_h, col_cell, row_cell, int(self.offset_x),
-                                                     int(self.offset_y), int(src_w), int(src_h))
-        blocks = build_row_blocks(row_cell, row_first, row0, row1)
+        gr, gc = inv_h.shape[0], inv_h.shape[1]
+        key = (col_cell.tobytes(), row_cell.tobytes(), gr, gc, int(row0), int(row1))
+        hit = getattr(self, "_warp_lut_cache", None)
+        if hit is None or hit[0] != key:
+            col_lut, row_first, col_ext, row_ext = warp_luts(col_cell, row_cell, gr, gc)
+            blocks = build_row_blocks(row_cell, row_first, row0, row1)
+            hit = (key, col_lut, blocks, col_ext, row_ext)
+            self._warp_lut_cache = hit
+        _, col_lut, blocks, col_ext, row_ext = hit
         hinv = np.ascontiguousarray(inv_h, dtype=np.float32).reshape(-1, 9)
         if not hasattr(self, "_warp_stage"):
             self._warp_stage = _PinnedStage()
-        views = self._warp_stage.upload(torch, device, (fast, hinv, col_lut, blocks))
-        return WarpTables(views[0].view(torch.float32), views[1].view(torch.float32),
-                          views[2].view(torch.int32), views[3].view(torch.int32), int(blocks.shape[0]),
-                          int(row0), int(row1), float((fast[:, 11] < 0).mean()))
+        views = self._warp_stage.upload(torch, device, (hinv, col_lut, blocks, col_ext, row_ext))
+        hinv_dev = views[0].view(torch.float32)
+        fast = torch.empty(gr * gc * HINV_ROW, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_warp_tables(hinv_dev.data_ptr(), views[3].data_ptr(), views[4].data_ptr(), gr, gc,
+                                          int(self.offset_x), int(self.offset_y), int(src_w), int(src_h),
+                                          fast.data_ptr(), rt.stream_ptr(torch, device)), "apap_warp_tables")
+        return WarpTables(fast, hinv_dev, views[1].view(torch.int32), views[2].view(torch.int32),
+                          int(blocks.shape[0]), int(row0), int(row1))
 
     def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False):
         """Device-resident K3 (optionally fused with K4): writes the canvas rows ``[tables.row0,
@@ -644,16 +698,17 @@ class APAP:
     def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False):
         mesh_n, pt_size, _, _ = local_homography.shape
         ori_h, ori_w, _ = ori_img.shape
-        # in-place per-cell inverse, stored back in the caller's array (pyviz/apap.py:201-203)
-        invert_grid_inplace(local_homography)
-        col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
         on_device = not isinstance(ori_img, np.ndarray)
         torch, device = rt.torch_cuda(ori_img.device if on_device else self.device)
+        # the image copies go first: they run (asynchronously, from pinned memory) under the host's LAPACK loop
         src_dev = ori_img.contiguous() if on_device else rt.to_device(torch, device, ori_img.astype(np.uint8, copy=False))
         centre_dev = None
         if centre_img is not None:
             centre_dev = (centre_img.contiguous() if not isinstance(centre_img, np.ndarray)
                           else rt.to_device(torch, device, centre_img.astype(np.uint8, copy=False)))
+        # in-place per-cell inverse, stored back in the caller's array (pyviz/apap.py:201-203)
+        invert_grid_inplace(local_homography)
+        col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
         tables = self.warp_tables_device(local_homography, col_cell, row_cell, ori_w, ori_h, device)
         out = self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)
         return out if on_device else rt.to_host(torch, out)

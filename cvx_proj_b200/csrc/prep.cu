@@ -1,0 +1,200 @@
+// Input preparation that used to run in numpy on the host and dominated the end-to-end time of the
+// public calls (measured at c2: ~6 ms of table building against a 33 us warp kernel; the per-cell inverse of
+// pyviz/apap.py:201-203 stays numpy's own LAPACK call on the host -- its float32 results are the float64 dgesv
+// of OpenBLAS rounded once, and no other arithmetic reproduces every bit of them):
+//   k_kp_blocks   keypoint row table -> tensor-core block table (host restatement: apap.build_kp_blocks)
+//   k_warp_prep   per-cell fast-path records of the mesh warp   (host restatement: apap.build_warp_tables)
+// The two kernels reproduce their numpy restatements bit for bit (explicit _rn arithmetic, no FMA
+// contraction, same operation order), so the CPU tests of the guard band cover the device-built tables.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace apap {
+
+// ------------------------------------------------------------------------------------ k_kp_blocks
+// Block layout (include/apap_b200.h): per 8 keypoints the 8 x 64 tile [Ph | Pl] in the K-major
+// core-matrix layout -- element (k, column m) at float (k/4)*256 + (m/8)*32 + (m%8)*4 + k%4 -- then
+// s*kx[8], s*ky[8].  Ph = P rounded to TF32 (ties away, like cvt.rna.tf32.f32), Pl = P - Ph (exact).
+__global__ void __launch_bounds__(256) k_kp_blocks(const float *__restrict__ table, int n_kb, float *__restrict__ out) {
+  const int kb = blockIdx.x;
+  const float *rows = table + (size_t)kb * APAP_KP_BLOCK * kRowFloats;
+  float *dst = out + (size_t)kb * APAP_KP_BLOCK_FLOATS;
+  for (int o = threadIdx.x; o < APAP_KP_BLOCK_FLOATS; o += blockDim.x) {
+    float v;
+    if (o < 512) {
+      const int j = o >> 8, r1 = (o >> 5) & 7, r0 = (o >> 2) & 7, kk = o & 3;
+      const int k = j * 4 + kk, m = r1 * 8 + r0, n = m & 31;
+      const float p = n < kTerms ? rows[k * kRowFloats + n] : 0.f;
+      const float hi = __uint_as_float((__float_as_uint(p) + 0x1000u) & 0xFFFFE000u);
+      v = m < 32 ? hi : __fsub_rn(p, hi);
+    } else if (o < 520) {
+      v = rows[(o - 512) * kRowFloats + 24];
+    } else {
+      v = rows[(o - 520) * kRowFloats + 26];
+    }
+    dst[o] = v;
+  }
+}
+
+int launch_kp_blocks(const float *table, int batch, int n_kp_padded, float *out, cudaStream_t st) {
+  const int n_kb = batch * (n_kp_padded / APAP_KP_BLOCK);
+  if (n_kb == 0) return 0;
+  k_kp_blocks<<<n_kb, 256, 0, st>>>(table, n_kb, out);
+  return check_cuda(cudaGetLastError(), "k_kp_blocks launch");
+}
+
+// ------------------------------------------------------------------------------------ k_warp_prep
+// One thread per cell.  See apap.build_warp_tables for the derivation: the cell's H^-1 rewritten
+// relative to the cell's first pixel and an integer base, scaled so the denominator is ~1, plus a
+// rigorous bound eps on the float32 quotient's error inside the cell.
+constexpr double kU = 5.9604644775390625e-08;          // 2^-24, float32 unit roundoff
+constexpr int kMagicBits = 0x4B400000;                 // float32 bits of 1.5 * 2^23
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double lin(double a, double x, double b, double y, double c) {   // (a x + b y) + c
+  return add(add(mul(a, x), mul(b, y)), c);
+}
+
+__global__ void __launch_bounds__(128) k_warp_prep(const float *__restrict__ inv_h, const int2 *__restrict__ col_ext,
+                                                    const int2 *__restrict__ row_ext, int grid_rows, int grid_cols,
+                                                    int off_x, int off_y, int src_w, int src_h,
+                                                    float *__restrict__ rec_out) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= grid_rows * grid_cols) return;
+  const int r = cell / grid_cols, c = cell - r * grid_cols;
+  int2 ce = col_ext[c], re = row_ext[r];               // {first, last} canvas column / row of the cell; first > last = unused
+  const bool col_used = ce.x <= ce.y, row_used = re.x <= re.y;
+  if (!col_used) ce = make_int2(0, 0);
+  if (!row_used) re = make_int2(0, 0);
+  double h[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = (double)inv_h[(size_t)cell * 9 + k];
+  const double x0 = (double)(ce.x - off_x), y0 = (double)(re.x - off_y);
+  const double dxm = (double)(ce.y - ce.x), dym = (double)(re.y - re.x);
+  bool ok = col_used && row_used;
+
+  const double t0 = lin(h[0], x0, h[1], y0, h[2]);
+  const double t1 = lin(h[3], x0, h[4], y0, h[5]);
+  const double t2 = lin(h[6], x0, h[7], y0, h[8]);
+  const double hx = mul(0.5, dxm), hy = mul(0.5, dym);
+  // integer base: the source position of the cell centre
+  const double c0 = add(add(t0, mul(h[0], hx)), mul(h[1], hy));
+  const double c1 = add(add(t1, mul(h[3], hx)), mul(h[4], hy));
+  const double c2 = add(add(t2, mul(h[6], hx)), mul(h[7], hy));
+  double bx = rint(dvd(c0, c2)), by = rint(dvd(c1, c2));
+  ok = ok && isfinite(bx) && isfinite(by) && fabs(bx) < 1073741824.0 && fabs(by) < 1073741824.0 && c2 != 0.0;
+  if (!ok) bx = by = 0.0;
+  const double s = ok ? dvd(1.0, c2) : 0.0;
+  double coef[9];
+  coef[0] = mul(sub(h[0], mul(bx, h[6])), s);
+  coef[1] = mul(sub(h[1], mul(bx, h[7])), s);
+  coef[2] = mul(sub(t0, mul(bx, t2)), s);
+  coef[3] = mul(sub(h[3], mul(by, h[6])), s);
+  coef[4] = mul(sub(h[4], mul(by, h[7])), s);
+  coef[5] = mul(sub(t1, mul(by, t2)), s);
+  coef[6] = mul(h[6], s);
+  coef[7] = mul(h[7], s);
+  coef[8] = mul(t2, s);
+  bool fin = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) fin = fin && isfinite(coef[k]);
+  ok = ok && fin;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) coef[k] = ok ? (double)(float)coef[k] : 0.0;   // what the warp kernel sees
+  double m[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m[k] = lin(fabs(coef[3 * k]), dxm, fabs(coef[3 * k + 1]), dym, fabs(coef[3 * k + 2]));
+  // corners of the cell's pixel rectangle, in the order (0,0) (0,dym) (dxm,0) (dxm,dym)
+  const double cx[4] = {mul(0.0, dxm), mul(0.0, dxm), dxm, dxm};
+  const double cy[4] = {mul(0.0, dym), dym, mul(0.0, dym), dym};
+  double corner[4], cmin = 0.0;
+  bool same_sign = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    corner[i] = lin(coef[6], cx[i], coef[7], cy[i], coef[8]);
+    same_sign = same_sign && corner[i] > 0.0;
+    cmin = i == 0 ? corner[0] : fmin(cmin, corner[i]);
+  }
+  const double d_err = mul(3.0 * kU, m[2]);
+  const double d_min = sub(cmin, d_err);               // the computed denominator is at least this
+  ok = ok && same_sign && d_min >= 0.25;
+  const double d_safe = ok ? d_min : 1.0;
+  double eps = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double q = dvd(m[k], d_safe);
+    const double e = add(dvd(add(mul(3.0 * kU, m[k]), mul(q, d_err)), d_safe), mul(q, 2.384185791015625e-07 + kU));
+    ok = ok && isfinite(q) && q < 1048576.0;
+    eps = fmax(eps, isfinite(e) ? e : 1.0);
+  }
+  eps = add(mul(1.25, eps), 1e-7);
+  ok = ok && eps < 0.25;
+  // cells that map entirely outside the source image: decided at the corners (the maps are ratios of
+  // functions affine in (dx, dy) with a positive denominator)
+  bool xl = true, xh = true, yl = true, yh = true;
+  const double wlim = (double)src_w + 0.5, hlim = (double)src_h + 0.5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double dc = ok ? corner[i] : 1.0;
+    const double qx = add(dvd(lin(coef[0], cx[i], coef[1], cy[i], coef[2]), dc), bx);
+    const double qy = add(dvd(lin(coef[3], cx[i], coef[4], cy[i], coef[5]), dc), by);
+    xl = xl && qx < -0.5; xh = xh && qx > wlim;
+    yl = yl && qy < -0.5; yh = yh && qy > hlim;
+  }
+  const bool outside = ok && (xl || xh || yl || yh);
+
+  float rec[kHinvRow];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rec[k] = ok ? (float)coef[k] : 0.f;
+  if (!ok) rec[8] = 1.f;
+  rec[9] = __int_as_float((int)((long long)(ok ? bx : 0.0) - (long long)kMagicBits));
+  rec[10] = __int_as_float((int)((long long)(ok ? by : 0.0) - (long long)kMagicBits));
+  const double hme = ok ? sub(0.5, eps) : -1.0;
+  float hme32 = (float)hme;
+  if ((double)hme32 > hme) hme32 = nextafterf(hme32, -2.f);   // round down
+  rec[11] = outside ? 2.f : hme32;                            // 2 = every pixel of the cell is left black
+  float4 *dst = reinterpret_cast<float4 *>(rec_out + (size_t)cell * kHinvRow);
+  dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+  dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+  dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+}
+
+int launch_warp_prep(const float *inv_h, const int *col_ext, const int *row_ext, int grid_rows, int grid_cols, int off_x,
+                     int off_y, int src_w, int src_h, float *rec_out, cudaStream_t st) {
+  const long long cells = (long long)grid_rows * grid_cols;
+  if (cells == 0) return 0;
+  if (cells > 2147483647LL / 12) return fail(APAP_E_TOOBIG, "warp tables: too many cells");
+  k_warp_prep<<<(unsigned)((cells + 127) / 128), 128, 0, st>>>(inv_h, reinterpret_cast<const int2 *>(col_ext),
+                                                               reinterpret_cast<const int2 *>(row_ext), grid_rows,
+                                                               grid_cols, off_x, off_y, src_w, src_h, rec_out);
+  return check_cuda(cudaGetLastError(), "k_warp_prep launch");
+}
+
+}  // namespace apap
+
+using namespace apap;
+
+extern "C" {
+
+int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream) {
+  if (!kp_table || !kp_blocks) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "kp_blocks: bad sizes");
+  return launch_kp_blocks(kp_table, batch, n_kp_padded, kp_blocks, static_cast<cudaStream_t>(stream));
+}
+
+int apap_warp_tables(const float *cell_hinv, const int *col_extent, const int *row_extent, int grid_rows, int grid_cols,
+                     int off_x, int off_y, int src_w, int src_h, float *cell_fast, void *stream) {
+  if (!cell_hinv || !col_extent || !row_extent || !cell_fast) return fail(APAP_E_BADARG, "null pointer");
+  if (grid_rows <= 0 || grid_cols <= 0) return fail(APAP_E_BADARG, "warp tables: bad grid");
+  if ((reinterpret_cast<uintptr_t>(cell_fast) & 15u) || (reinterpret_cast<uintptr_t>(col_extent) & 7u) ||
+      (reinterpret_cast<uintptr_t>(row_extent) & 7u))
+    return fail(APAP_E_ALIGN, "warp tables: cell_fast must be 16-byte, the extents 8-byte aligned");
+  return launch_warp_prep(cell_hinv, col_extent, row_extent, grid_rows, grid_cols, off_x, off_y, src_w, src_h, cell_fast,
+                          static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

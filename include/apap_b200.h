@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 3
+#define APAP_ABI_VERSION 4
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -148,6 +148,25 @@ int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, 
  * per pixel of n_px 3-byte pixels.  All three pointers 16-byte aligned.
  */
 int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream);
+
+/*
+ * Input preparation on the device (what the host layer used to build in numpy; both reproduce their
+ * numpy restatements in cvx_proj_b200/apap.py bit for bit).
+ *
+ * apap_kp_blocks: the keypoint row table of engine FFMA2 -> the block table of engine TCGEN05 (layouts under
+ * apap_gram_partials; the TF32 split of the product terms pyviz/apap.py:106-118 feeds the tensor cores).
+ *   kp_table : float [batch][n_kp_padded][APAP_KP_ROW];  kp_blocks : float [batch][n_kp_padded / 8][APAP_KP_BLOCK_FLOATS]
+ *
+ * apap_warp_tables: the fast-path records `cell_fast` of apap_warp from the inverted grid (the per-pixel
+ * arithmetic of pyviz/apap.py:211-215 rewritten per cell, with its error bound).
+ *   cell_hinv  : float [grid_rows*grid_cols][9], the inverted grid of pyviz/apap.py:201-203
+ *   col_extent : int32 [grid_cols][2] = {first, last} canvas column mapped to the cell column by the
+ *                reference's lookup (pyviz/apap.py:209), first > last = no canvas column; row_extent alike
+ *   cell_fast  : float [grid_rows*grid_cols][APAP_HINV_ROW] (out)
+ */
+int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream);
+int apap_warp_tables(const float *cell_hinv, const int *col_extent, const int *row_extent, int grid_rows,
+                     int grid_cols, int off_x, int off_y, int src_w, int src_h, float *cell_fast, void *stream);
 
 /*
  * Pipe probes for the roofline denominators that MEASURED_PEAKS.json does not hold.  Runs `iters` x 16

@@ -187,6 +187,50 @@ def test_gram_engines_agree_on_partial_sums():
     assert err.max() <= 2e-5
 
 
+@pytest.mark.parametrize("n_kp", [5, 128, 1000, 2049])
+def test_device_kp_blocks_equal_host_restatement(n_kp):
+    """apap_kp_blocks packs the tensor-core block table on the device: same bits as build_kp_blocks."""
+    import torch
+    from cvx_proj_b200.apap import build_kp_blocks
+    sc = synth.make_scene("mini", n_kp=n_kp, mesh=4)
+    st = _stitcher(sc)
+    table, _ = st._prepare(sc.src, sc.dst)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = torch.from_numpy(np.stack([table, table[::-1].copy()])).to(dev)          # batch of 2
+    got = st.kp_table_device(rows).cpu().numpy()
+    for b, tab in enumerate((table, table[::-1].copy())):
+        want = build_kp_blocks(tab)
+        assert got[b].shape == want.shape
+        assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32))
+
+
+def test_device_warp_tables_equal_host_restatement():
+    """apap_warp_tables builds the fast-path records on the device: same bits as build_warp_tables (whose
+    guard-band logic the CPU tests check), on a real grid and on degenerate / adversarial cells."""
+    import torch
+    from cvx_proj_b200.apap import build_warp_tables
+    for name, kw in (("mini", {}), ("c1", {}), ("mini", {"mesh": 300})):      # mesh 300 > canvas: unused cells
+        sc = synth.make_scene(name, **kw)
+        st = _stitcher(sc)
+        m = sc.mesh_cells
+        rng = np.random.default_rng(5)
+        h = np.linalg.inv(sc.h_gt)[None, None].repeat(m, 0).repeat(m, 1)
+        h = (h * (1 + 1e-3 * rng.standard_normal(h.shape))).astype(np.float32)
+        h[0, 0] = 0                                   # degenerate cells
+        h[1 % m, 2 % m] = np.nan
+        h[2 % m, 1 % m, 2] = [1e-30, 1e-30, 1e-30]    # denominator ~ 0
+        h[3 % m, 3 % m] *= -1                         # negative denominator
+        h[4 % m, 0] = np.eye(3, dtype=np.float32)     # exact integer hits
+        h[m - 1, m - 1, :, 2] += 1e9                  # far outside / beyond 2^30
+        col, row = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, m, m)
+        want, _, _ = build_warp_tables(h, col, row, sc.offset_x, sc.offset_y, sc.width, sc.height)
+        tabs = st.warp_tables_device(h, col, row, sc.width, sc.height)
+        got = tabs.cell_fast.cpu().numpy().reshape(-1, 12)
+        same = got.view(np.uint32) == want.view(np.uint32)
+        assert same.all(), (name, kw, np.argwhere(~same)[:5], got[~same.all(1)][:2], want[~same.all(1)][:2])
+        assert 0.0 <= tabs.exact_cells_frac() <= 1.0
+
+
 def test_eig_solvers_agree_and_report():
     """AUTO (float64 LDL^T inverse iteration) and JACOBI (full FP32 diagonalisation) give the same
     grid; out_sweeps tells which one ran per cell."""
@@ -196,7 +240,7 @@ def test_eig_solvers_agree_and_report():
     st = _stitcher(sc)
     table, tmats = st._prepare(sc.src, sc.dst)
     dev = torch.device("cuda", torch.cuda.current_device())
-    t = torch.from_numpy(table[None]).to(dev)
+    t = st.kp_table_device(torch.from_numpy(table[None]).to(dev))
     a = torch.from_numpy(scale_anchors(sc.vertices, weight_scale(sc.sigma))[None]).to(dev)
     m = torch.from_numpy(tmats[None]).to(dev)
     cells = 40 * 40
@@ -378,6 +422,25 @@ def test_uniform_blend_full_size_properties():
     assert np.array_equal(apap_utils.uniform_blend(b, a), out)                      # symmetric
     assert np.array_equal(apap_utils.uniform_blend(a, np.zeros_like(a)), a)        # black is neutral
     assert np.array_equal(apap_utils.uniform_blend(a, a), np.where(a.max(-1, keepdims=True) > 0, a, 0))
+
+
+def test_stitch_pair_driver_vs_oracle_pipeline():
+    """The script from its matched keypoints on (pyviz/apap.py:238-265): grid, .mat matrix, stitched image."""
+    from cvx_proj_b200 import driver
+    sc = synth.make_scene("mini")
+    other, centre = sc.image(1), synth.make_image(sc.width, sc.height, seed=2)
+    res = driver.stitch_pair(centre, other, sc.src, sc.dst, sc.h_gt, mesh_size=sc.mesh_cells, gamma=sc.gamma,
+                             sigma=sc.sigma)
+    assert res.final_size == (sc.final_w, sc.final_h, sc.offset_x, sc.offset_y)
+    assert np.array_equal(res.mesh, sc.mesh) and np.array_equal(res.vertices, sc.vertices)
+    ref = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+    assert _herr(res.local_homography, ref, sc).max() <= H_GATE
+    # the .mat matrix and the image are functions of the float32 grid we returned: bit-exact against the oracle
+    assert np.array_equal(res.mat, orc.mat_layout(res.local_homography))
+    inv = orc.invert_grid(res.local_homography)
+    warped = orc.local_warp(other, inv, sc.mesh, (sc.final_w, sc.final_h), (sc.offset_x, sc.offset_y))
+    want = orc.uniform_blend(warped, orc.paste_centre(warped, centre, (sc.offset_x, sc.offset_y)))
+    assert np.array_equal(res.stitched, want)
 
 
 def test_errors_surface_as_exceptions():

@@ -293,7 +293,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 3
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 4
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 
@@ -363,3 +363,22 @@ def test_band_gather_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+# ---------------------------------------------------------------------------- driver pieces (N1)
+@pytest.mark.parametrize("name", ["tiny", "mini"])
+def test_mat_layout_bit_exact_vs_reference_and_in_place(golden, name, tmp_path):
+    """pyviz/apap.py:250-265: the reference's own post-processing output is in the golden file ('mat')."""
+    import scipy.io
+    from cvx_proj_b200 import driver
+    g = golden(f"ref_{name}.npz")
+    grid = g["H"].copy()
+    mat = driver.mat_layout(grid)
+    assert mat.dtype == np.float64 and mat.shape == (grid.shape[0] * grid.shape[1], 9)
+    assert np.array_equal(mat, g["mat"])
+    # the caller's grid now holds the normalised inverses, like the script's loop leaves it
+    assert np.array_equal(grid.transpose(0, 1, 3, 2).astype(np.float64).reshape(-1, 9), mat)
+    assert np.all(grid[..., 2, 2] == 1.0)
+    path = driver.save2mat("H31_apap", mat, name="H", prefix=str(tmp_path) + "/")
+    back = scipy.io.loadmat(path)
+    assert np.array_equal(back["H"], mat)

@@ -19,12 +19,12 @@ tag = os.path.basename(os.environ.get("APAP_B200_LIB", "product"))
 for spec in sys.argv[1:]:
     cells, n_kp = (int(v) for v in spec.split(":"))
     src, dst, _ = synth.make_keypoints(3840, 2160, n_kp, seed=0)
-    st = APAP(0.5, 100, [4448, 2332], [0, 0], device=dev)
+    st = APAP(0.5, 100, [4448, 2332], [0, 0], device=dev)  # tcgen05 engine
     table, tmats = st._prepare(src, dst)
     rng = np.random.default_rng(1)
     verts = rng.uniform([0, 0], [4448, 2332], size=(cells, 1, 2))
-    n_pad = table.shape[0] * rt.KP_BLOCK
-    t_dev = torch.from_numpy(table).to(dev)
+    n_pad = table.shape[0]
+    t_dev = st.kp_table_device(torch.from_numpy(table[None]).to(dev))[0]
     a_dev = torch.from_numpy(scale_anchors(verts, weight_scale(100))).to(dev)
     ks, cp, nbytes = rt.gram_plan(cells, n_pad)
     partials = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
