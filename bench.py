@@ -232,7 +232,7 @@ class Pass:
         self.table = self.st.kp_table_device(self.rows)[0]                   # the engine's table (blocks for tcgen05)
         self.anchors = torch.from_numpy(scale_anchors(verts, weight_scale(sc.sigma))).to(device)
         self.tmats = torch.from_numpy(tmats).to(device)
-        self.k_splits, self.cells_padded, nbytes = rt.gram_plan(self.cells, self.n_pad)
+        self.k_splits, self.cells_padded, nbytes = rt.gram_plan(self.cells, self.n_pad, self.engine)
         self.partials = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
         self.h_out = torch.empty((self.cells, 9), dtype=torch.float32, device=device)
         self.g2 = float(np.float32(float(sc.gamma) ** 2))
@@ -247,7 +247,7 @@ class Pass:
 
     def eig(self):
         self.rt.check(self.lib.apap_eig_denorm(self.partials.data_ptr(), self.tmats.data_ptr(), 1, self.cells,
-                                               self.n_pad, self.rt.EIG_AUTO, self.h_out.data_ptr(), None, self.stream),
+                                               self.k_splits, self.rt.EIG_AUTO, self.h_out.data_ptr(), None, self.stream),
                       "eig")
 
     # -- warp

@@ -19,7 +19,7 @@ KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
 WARP_BLOCK_ROWS = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 KP_BLOCK = 8
 KP_BLOCK_FLOATS = 528
 GRAM_TCGEN05 = 0
@@ -32,7 +32,7 @@ SIGNATURES = {
     "apap_abi_version": (c_int, []),
     "apap_last_error": (c_char_p, []),
     "apap_device_sm_count": (c_int, [POINTER(c_int)]),
-    "apap_gram_plan": (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
+    "apap_gram_plan": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "apap_gram_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "apap_eig_denorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int,
@@ -81,11 +81,11 @@ def check(rc: int, what: str = ""):
         raise ApapError(f"libapap_b200 {what} failed (code {rc}): {msg}")
 
 
-def gram_plan(cells: int, n_kp_padded: int):
+def gram_plan(cells: int, n_kp_padded: int, engine: int = GRAM_TCGEN05):
     """(k_splits, cells_padded, partial_bytes_per_scene) -- pure host arithmetic, no GPU needed."""
     lib = load_library()
     ks, cp, nb = c_int(), c_int(), c_size_t()
-    check(lib.apap_gram_plan(int(cells), int(n_kp_padded), ctypes.byref(ks), ctypes.byref(cp), ctypes.byref(nb)),
+    check(lib.apap_gram_plan(int(cells), int(n_kp_padded), int(engine), ctypes.byref(ks), ctypes.byref(cp), ctypes.byref(nb)),
           "apap_gram_plan")
     return ks.value, cp.value, nb.value
 

@@ -585,7 +585,7 @@ class APAP:
         lib = rt.load_library()
         engine = rt.GRAM_TCGEN05 if table_dev.shape[-1] == KP_BLOCK_FLOATS else rt.GRAM_FFMA2
         n_pad = table_dev.shape[-2] * (KP_BLOCK if engine == rt.GRAM_TCGEN05 else 1)
-        _, _, nbytes = rt.gram_plan(cells, n_pad)
+        _, _, nbytes = rt.gram_plan(cells, n_pad, engine)
         if partials is None:
             partials = torch.empty(batch * nbytes // 4, dtype=torch.float32, device=device)
         if out_h is None:

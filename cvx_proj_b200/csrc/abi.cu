@@ -47,10 +47,12 @@ int apap_device_sm_count(int *sm_count) {
   return 0;
 }
 
-int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded, size_t *partial_bytes_per_scene) {
+int apap_gram_plan(int cells, int n_kp_padded, int engine, int *k_splits, int *cells_padded,
+                   size_t *partial_bytes_per_scene) {
+  if (engine != APAP_GRAM_TCGEN05 && engine != APAP_GRAM_FFMA2) return fail(APAP_E_BADARG, "gram_plan: unknown engine");
   if (cells <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "gram_plan: bad sizes");
   // the layout (k_splits, cells_padded) does not depend on the SM count; only the register tile does
-  const GramPlan p = make_gram_plan(cells, n_kp_padded, 148);
+  const GramPlan p = make_gram_plan(cells, n_kp_padded, engine);
   if (k_splits) *k_splits = p.k_splits;
   if (cells_padded) *cells_padded = p.cells_padded;
   if (partial_bytes_per_scene) *partial_bytes_per_scene = (size_t)p.k_splits * kTerms * p.cells_padded * sizeof(float);
@@ -70,12 +72,12 @@ int apap_gram_partials(const float *kp_table, const float *anchors, int batch, i
                      static_cast<cudaStream_t>(stream));
 }
 
-int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded, int solver,
+int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells, int k_splits, int solver,
                     float *out_h, int *out_sweeps, void *stream) {
   if (!partials || !tmats || !out_h) return fail(APAP_E_BADARG, "null pointer");
-  if (batch <= 0 || cells <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "eig: bad sizes");
+  if (batch <= 0 || cells <= 0 || k_splits <= 0) return fail(APAP_E_BADARG, "eig: bad sizes");
   if (solver != APAP_EIG_AUTO && solver != APAP_EIG_JACOBI) return fail(APAP_E_BADARG, "eig: unknown solver");
-  return launch_eig(partials, tmats, batch, cells, n_kp_padded, out_h, out_sweeps, solver == APAP_EIG_JACOBI,
+  return launch_eig(partials, tmats, batch, cells, k_splits, out_h, out_sweeps, solver == APAP_EIG_JACOBI,
                     static_cast<cudaStream_t>(stream));
 }
 
@@ -84,7 +86,8 @@ int apap_local_homography(const float *kp_table, const float *anchors, const dou
                           float *partials, float *out_h, int *out_sweeps, void *stream) {
   int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, engine, partials, stream);
   if (rc) return rc;
-  return apap_eig_denorm(partials, tmats, batch, cells, n_kp_padded, solver, out_h, out_sweeps, stream);
+  return apap_eig_denorm(partials, tmats, batch, cells, make_gram_plan(cells, n_kp_padded, engine).k_splits, solver, out_h,
+                         out_sweeps, stream);
 }
 
 int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,

@@ -20,7 +20,13 @@ constexpr int kHinvRow = APAP_HINV_ROW;     // 12 floats = 48 B per cell
 #ifndef APAP_MAX_CHAIN_CHUNKS
 #define APAP_MAX_CHAIN_CHUNKS 8
 #endif
-constexpr int kMaxChainChunks = APAP_MAX_CHAIN_CHUNKS;   // 8 x 128 = 1024 keypoints per split
+constexpr int kMaxChainChunks = APAP_MAX_CHAIN_CHUNKS;   // FFMA2 engine: 8 x 128 = 1024 keypoints per split
+// The tensor-core engine never runs an FP32 chain longer than a 256-keypoint segment (its splits only exist for
+// parallelism), so its splits may be longer: fewer partial planes for K2 to read (c3: 311 -> 156 MB).
+#ifndef APAP_MAX_SPLIT_CHUNKS_TC
+#define APAP_MAX_SPLIT_CHUNKS_TC 16
+#endif
+constexpr int kMaxSplitChunksTc = APAP_MAX_SPLIT_CHUNKS_TC;   // 16 x 128 = 2048 keypoints per split
 
 struct GramPlan {
   int k_splits;
@@ -30,7 +36,7 @@ struct GramPlan {
   int cell_tiles;
 };
 
-GramPlan make_gram_plan(int cells, int n_kp_padded, int sm_count);
+GramPlan make_gram_plan(int cells, int n_kp_padded, int engine);
 int sm_count_cached();
 
 // error plumbing (abi.cu)
@@ -42,7 +48,7 @@ int launch_gram(const float *kp_table, const float *anchors, int batch, int cell
                 float gamma_sq, float *partials, cudaStream_t st);
 int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded,
                    float gamma_sq, float *partials, cudaStream_t st);
-int launch_eig(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded,
+int launch_eig(const float *partials, const double *tmats, int batch, int cells, int k_splits,
                float *out_h, int *out_sweeps, int force_jacobi, cudaStream_t st);
 int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
                   double gamma, double *out, cudaStream_t st);

@@ -278,12 +278,12 @@ __global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ p
   if (sw) *sw = -iters;                                 // negative: inverse-iteration steps used
 }
 
-int launch_eig(const float *partials, const double *tmats, int batch, int cells, int n_kp_padded, float *out_h,
+int launch_eig(const float *partials, const double *tmats, int batch, int cells, int k_splits, float *out_h,
                int *out_sweeps, int force_jacobi, cudaStream_t st) {
-  const GramPlan p = make_gram_plan(cells, n_kp_padded, sm_count_cached());
+  const int cells_padded = make_gram_plan(cells, kChunk, APAP_GRAM_FFMA2).cells_padded;   // depends on cells only
   dim3 grid((cells + kEigThreads - 1) / kEigThreads, batch);
   if (batch > 65535) return fail(APAP_E_TOOBIG, "eig: batch exceeds 65535");
-  k_eig<<<grid, kEigThreads, 0, st>>>(partials, tmats, cells, p.cells_padded, p.k_splits, force_jacobi, out_h,
+  k_eig<<<grid, kEigThreads, 0, st>>>(partials, tmats, cells, cells_padded, k_splits, force_jacobi, out_h,
                                       out_sweeps);
   return check_cuda(cudaGetLastError(), "k_eig launch");
 }

@@ -42,13 +42,13 @@ int sm_count_cached() {
   return g_sm_count;
 }
 
-GramPlan make_gram_plan(int cells, int n_kp_padded, int sm_count) {
-  (void)sm_count;
+GramPlan make_gram_plan(int cells, int n_kp_padded, int engine) {
   GramPlan p;
   const int n_chunks = n_kp_padded / kChunk;
   int cps = (n_chunks + 3) / 4;                 // a function of N only (see header comment)
   if (cps < 1) cps = 1;
-  if (cps > kMaxChainChunks) cps = kMaxChainChunks;
+  const int cap = engine == APAP_GRAM_TCGEN05 ? kMaxSplitChunksTc : kMaxChainChunks;
+  if (cps > cap) cps = cap;
   p.chunks_per_split = cps;
   p.k_splits = (n_chunks + cps - 1) / cps;
   if (p.k_splits < 1) p.k_splits = 1;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kGramThreads, 12) k_gram(const float *__restri
 
 int launch_gram(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded, float gamma_sq,
                 float *partials, cudaStream_t st) {
-  const GramPlan p = make_gram_plan(cells, n_kp_padded, sm_count_cached());
+  const GramPlan p = make_gram_plan(cells, n_kp_padded, APAP_GRAM_FFMA2);
   const int n_chunks = n_kp_padded / kChunk;
   dim3 grid(p.cell_tiles, p.k_splits, batch);
   if (p.k_splits > 65535 || batch > 65535) return fail(APAP_E_TOOBIG, "gram: grid.y/z exceeds 65535");

@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
 
 int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded, float gamma_sq,
                    float *partials, cudaStream_t st) {
-  const GramPlan p = make_gram_plan(cells, n_kp_padded, sm_count_cached());
+  const GramPlan p = make_gram_plan(cells, n_kp_padded, APAP_GRAM_TCGEN05);
   const int n_kb = n_kp_padded / kKB;
   const int kb_per_split = p.chunks_per_split * (kChunk / kKB);
   dim3 grid((cells + 127) / 128, p.k_splits, batch);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 4
+#define APAP_ABI_VERSION 5
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -49,11 +49,16 @@ const char *apap_last_error(void);
 int apap_device_sm_count(int *sm_count);
 
 /*
- * Plan the moving-DLT contraction: how many keypoint splits the Gram kernel uses for
- * (cells, n_kp_padded) and how many bytes of partial sums it needs per scene.
+ * Plan the moving-DLT contraction: how many keypoint splits the Gram kernel of `engine` uses for
+ * n_kp_padded keypoints (a function of the keypoint count and the engine only, so a grid computed in
+ * row shards equals the unsharded grid bit for bit) and how many bytes of partial sums it needs per scene.
  *   partial layout: float [k_splits][APAP_GRAM_TERMS][cells_padded]   (term-major, coalesced)
+ *   engine FFMA2: a split is at most 1024 keypoints, the longest FP32 chain the kernel runs before the
+ *   float64 combine of K2; engine TCGEN05 (chains of 256 keypoints whatever the split): at most 2048.
  */
-int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
+#define APAP_GRAM_TCGEN05 0
+#define APAP_GRAM_FFMA2   1
+int apap_gram_plan(int cells, int n_kp_padded, int engine, int *k_splits, int *cells_padded,
                    size_t *partial_bytes_per_scene);
 
 /*
@@ -75,14 +80,12 @@ int apap_gram_plan(int cells, int n_kp_padded, int *k_splits, int *cells_padded,
  *   partials : float [batch][k_splits][24][cells_padded]  (same layout for both engines)
  *   gamma_sq = gamma^2
  */
-#define APAP_GRAM_TCGEN05 0
-#define APAP_GRAM_FFMA2   1
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells,
                        int n_kp_padded, float gamma_sq, int engine, float *partials, void *stream);
 
 /*
  * K2 -- per-cell 9x9 symmetric eigensolve + de-normalisation.  Replaces cv.SVDecomp + V[-1]
- * (pyviz/apap.py:160-161) and pyviz/apap.py:164-168: sums the k_splits partials in float64,
+ * (pyviz/apap.py:160-161) and pyviz/apap.py:164-168: sums the k_splits partials (apap_gram_plan) in float64,
  * expands the 24 sums to the 9x9 Gram matrix, finds the eigenvector h of its smallest eigenvalue
  * and stores float32 H = T2inv * reshape(h,3,3) * T1, divided by H[2][2].
  *   solver : APAP_EIG_AUTO = float64 LDL^T inverse iteration, cyclic Jacobi for the cells whose
@@ -95,7 +98,7 @@ int apap_gram_partials(const float *kp_table, const float *anchors, int batch, i
 #define APAP_EIG_AUTO   0
 #define APAP_EIG_JACOBI 1
 int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells,
-                    int n_kp_padded, int solver, float *out_h, int *out_sweeps, void *stream);
+                    int k_splits, int solver, float *out_h, int *out_sweeps, void *stream);
 
 /* K1 + K2 back to back on `stream` (what APAP.local_homography calls). */
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats,

@@ -171,10 +171,10 @@ def test_gram_engines_agree_on_partial_sums():
     lib = rt.load_library()
     dev = torch.device("cuda", torch.cuda.current_device())
     cells, n_pad = 37 * 37, table.shape[0]
-    ks, cp, nbytes = rt.gram_plan(cells, n_pad)
     a = torch.from_numpy(scale_anchors(sc.vertices, weight_scale(sc.sigma))).to(dev)
     out = {}
     for engine, tab in ((rt.GRAM_FFMA2, table), (rt.GRAM_TCGEN05, build_kp_blocks(table))):
+        ks, cp, nbytes = rt.gram_plan(cells, n_pad, engine)
         t = torch.from_numpy(tab).to(dev)
         part = torch.zeros(nbytes // 4, dtype=torch.float32, device=dev)
         rt.check(lib.apap_gram_partials(t.data_ptr(), a.data_ptr(), 1, cells, n_pad, 0.25, engine, part.data_ptr(),

@@ -275,14 +275,18 @@ def test_guard_band_degenerate_cells_go_exact():
 
 def test_gram_plan_depends_only_on_keypoints():
     seen = {}
-    for cells in (64, 10_000, 40_000, 160_000):
-        for n_pad in (128, 512, 2048, 5120, 20096, 65536):
-            ks, cp, nb = rt.gram_plan(cells, n_pad)
-            assert seen.setdefault(n_pad, ks) == ks          # same split structure however the grid is sharded
-            assert cp >= cells and cp % 512 == 0 and nb == ks * 24 * cp * 4
-            assert -(-n_pad // ks) <= 1024 + 128             # FP32 chains stay <= 1024 keypoints (+ rounding to a chunk)
+    for engine, longest in ((rt.GRAM_FFMA2, 1024), (rt.GRAM_TCGEN05, 2048)):
+        for cells in (64, 10_000, 40_000, 160_000):
+            for n_pad in (128, 512, 2048, 5120, 20096, 65536):
+                ks, cp, nb = rt.gram_plan(cells, n_pad, engine)
+                assert seen.setdefault((engine, n_pad), ks) == ks   # same split structure however the grid is sharded
+                assert cp >= cells and cp % 512 == 0 and nb == ks * 24 * cp * 4
+                assert -(-n_pad // ks) <= longest + 128       # FFMA2: FP32 chains stay <= 1024 keypoints (+ chunk rounding)
+    assert rt.gram_plan(160_000, 20096, rt.GRAM_TCGEN05)[0] < rt.gram_plan(160_000, 20096, rt.GRAM_FFMA2)[0]
     with pytest.raises(rt.ApapError):
         rt.gram_plan(10, 100)                                # not a multiple of the chunk
+    with pytest.raises(rt.ApapError):
+        rt.gram_plan(10, 128, 7)                             # unknown engine
 
 
 def test_library_exports_every_declared_symbol():
@@ -293,7 +297,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 4
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 5
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 

@@ -26,7 +26,7 @@ for spec in sys.argv[1:]:
     n_pad = table.shape[0]
     t_dev = st.kp_table_device(torch.from_numpy(table[None]).to(dev))[0]
     a_dev = torch.from_numpy(scale_anchors(verts, weight_scale(100))).to(dev)
-    ks, cp, nbytes = rt.gram_plan(cells, n_pad)
+    ks, cp, nbytes = rt.gram_plan(cells, n_pad, rt.GRAM_TCGEN05)
     partials = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
     s = rt.stream_ptr(torch, dev)
     ts = []
