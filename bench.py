@@ -245,6 +245,12 @@ class Pass:
                                                   self.n_pad, self.g2, self.engine, self.partials.data_ptr(),
                                                   self.stream), "gram")
 
+    def dlt(self, overlap=True):
+        """K1 + K2 as the public call launches them (K2 a programmatic dependent of K1 when ``overlap``)."""
+        self.st.local_homography_device(self.table[None], self.anchors[None], self.tmats[None], 1, self.cells,
+                                        out_h=self.h_out[None] if self.h_out.dim() == 2 else self.h_out,
+                                        partials=self.partials, overlap=overlap)
+
     def eig(self):
         self.rt.check(self.lib.apap_eig_denorm(self.partials.data_ptr(), self.tmats.data_ptr(), 1, self.cells,
                                                self.k_splits, self.rt.EIG_AUTO, self.h_out.data_ptr(), None, self.stream),
@@ -352,11 +358,14 @@ def run_ours(args):
     def dlt_body(mark):
         mark(); p.gram(); mark(); p.eig(); mark()
     barrier()
-    t_gram, t_eig = timed_steps(torch, flush, W, K, dlt_body, 3)
+    t_gram, t_eig = timed_steps(torch, flush, W, K, dlt_body, 3)        # K1, K2 timed one by one (roofline attribution)
     barrier()
-    launches += 2 * K
-    ms_dlt = max_over_ranks(t_gram + t_eig)
+    (t_dlt,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.dlt(), mark()), 2)   # the stage as the public call launches it
+    barrier()
+    launches += 4 * K
+    ms_dlt = max_over_ranks(t_dlt)
     ms_gram = max_over_ranks(t_gram)
+    ms_eig = max_over_ranks(t_eig)
     cells_total = p.cells * world
     value = cells_total / (ms_dlt * 1e-3)
 
@@ -449,13 +458,15 @@ def run_ours(args):
                            "frac": mma_flops / gram_s / 1e12 / tf32_peak,
                            "what": "executed TF32 MMA flop (3xTF32, N padded to 32) against bf16_tflops / 2 "
                                    "of MEASURED_PEAKS.json"},
-                "fp32_equivalent": fp32_equiv, "ms": ms_gram, "eig_ms": ms_dlt - ms_gram}
+                "fp32_equivalent": fp32_equiv, "ms": ms_gram, "eig_ms": ms_eig,
+                "stage_note": "ms / eig_ms: K1 and K2 launched and timed one by one; the stage (ms_per_step, value) is the "
+                              "public call's launch, K2 a programmatic dependent of K1 that starts on finished cell tiles"}
     else:
         roof = {"kernel": "k_gram", "bound": "fp32_fma", "achieved": fp32_equiv["achieved"], "peak": fp32_peak,
                 "unit": "TFLOP/s", "frac": fp32_equiv["frac"], "traffic": traffic.get("k_gram"),
                 "peak_source": "FP32 FFMA probe kernel timed in this run (not in MEASURED_PEAKS.json)",
                 "algorithmic": "2*24*n_kp_padded*cells flop per launch (24 executed terms)",
-                "ms": ms_gram, "eig_ms": ms_dlt - ms_gram}
+                "ms": ms_gram, "eig_ms": ms_eig}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dlt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -514,6 +525,8 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
     barrier()
     t_gram, t_eig = timed_steps(torch, flush, W, K, dlt_body, 3)
     barrier()
+    (t_dlt,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.dlt(), mark()), 2)
+    barrier()
     p.prepare_warp(px_rows=(me.px_row0, me.px_row1))
     barrier()
     (t_warp,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(False), mark()), 2)
@@ -524,7 +537,7 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
             mark(); sharding.gather_bands(p.canvas, shards, sc0.final_w); mark()
         (t_gather,) = timed_steps(torch, flush, W, K, gather_body, 2)
         barrier()
-    ms_dlt = max_over_ranks(t_gram + t_eig)
+    ms_dlt = max_over_ranks(t_dlt)
     ms_warp = max_over_ranks(t_warp)
     ms_gather = max_over_ranks(t_gather)
     return {"workload": _workload_desc("c3"), "scaling": "strong", "n_gpus": world,
@@ -532,7 +545,7 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
             "warp_mpix_per_s": sc0.canvas_px / (ms_warp * 1e-3) / 1e6, "warp_ms": ms_warp,
             "allgather_ms": ms_gather, "allgather_bytes": 3 * sc0.canvas_px,
             "shard": "cell rows + canvas row bands per rank; keypoints and source image replicated",
-            "_launches": 3 * K}
+            "_launches": 5 * K}
 
 
 def main():

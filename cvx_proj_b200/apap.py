@@ -576,11 +576,23 @@ class APAP:
                                         rt.stream_ptr(torch, device)), "apap_kp_blocks")
         return blocks
 
+    def _tile_counters(self, torch, device, batch, cells):
+        """Zeroed int32 scratch ``[batch, ceil(cells / 128)]`` for the overlapped K1 -> K2 launch (the library
+        leaves it zero after every completed call, so it is allocated and cleared once per shape)."""
+        key = (str(device), batch, (cells + 127) // 128)
+        hit = getattr(self, "_counters", None)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.zeros((batch, (cells + 127) // 128), dtype=torch.int32, device=device))
+            self._counters = hit
+        return hit[1]
+
     def local_homography_device(self, table_dev, anchors_dev, tmats_dev, batch, cells, out_h=None, partials=None,
-                                sweeps=None, solver=rt.EIG_AUTO):
+                                sweeps=None, solver=rt.EIG_AUTO, overlap=True):
         """Device-resident K1 + K2 (no host traffic): tensors in, ``[batch, cells, 9]`` float32 out.
         ``table_dev`` / ``anchors_dev`` hold pre-scaled coordinates (``build_kp_table`` or, for the
-        tensor-core engine, ``build_kp_blocks``; ``scale_anchors``); the engine follows from the table's shape."""
+        tensor-core engine, ``build_kp_blocks``; ``scale_anchors``); the engine follows from the table's shape.
+        ``overlap``: launch K2 as a programmatic dependent of K1 (it starts on finished cell tiles while K1's last
+        CTAs are still running); same results either way."""
         torch, device = rt.torch_cuda(table_dev.device)
         lib = rt.load_library()
         engine = rt.GRAM_TCGEN05 if table_dev.shape[-1] == KP_BLOCK_FLOATS else rt.GRAM_FFMA2
@@ -593,7 +605,9 @@ class APAP:
         with torch.cuda.device(device):
             rt.check(lib.apap_local_homography(
                 table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
-                float(np.float32(float(self.gamma) ** 2)), engine, int(solver), partials.data_ptr(), out_h.data_ptr(),
+                float(np.float32(float(self.gamma) ** 2)), engine, int(solver), partials.data_ptr(),
+                self._tile_counters(torch, device, batch, cells).data_ptr()
+                if overlap and engine == rt.GRAM_TCGEN05 else None, out_h.data_ptr(),
                 sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
                 "apap_local_homography")
         return out_h

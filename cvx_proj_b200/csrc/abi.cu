@@ -65,7 +65,7 @@ int apap_gram_partials(const float *kp_table, const float *anchors, int batch, i
   if (rc) return rc;
   if (!partials) return fail(APAP_E_BADARG, "null partials");
   if (engine == APAP_GRAM_TCGEN05)
-    return launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials,
+    return launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials, nullptr,
                           static_cast<cudaStream_t>(stream));
   if (engine != APAP_GRAM_FFMA2) return fail(APAP_E_BADARG, "gram: unknown engine");
   return launch_gram(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials,
@@ -77,17 +77,28 @@ int apap_eig_denorm(const float *partials, const double *tmats, int batch, int c
   if (!partials || !tmats || !out_h) return fail(APAP_E_BADARG, "null pointer");
   if (batch <= 0 || cells <= 0 || k_splits <= 0) return fail(APAP_E_BADARG, "eig: bad sizes");
   if (solver != APAP_EIG_AUTO && solver != APAP_EIG_JACOBI) return fail(APAP_E_BADARG, "eig: unknown solver");
-  return launch_eig(partials, tmats, batch, cells, k_splits, out_h, out_sweeps, solver == APAP_EIG_JACOBI,
+  return launch_eig(partials, tmats, batch, cells, k_splits, out_h, out_sweeps, solver == APAP_EIG_JACOBI, nullptr,
                     static_cast<cudaStream_t>(stream));
 }
 
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats, int batch, int cells,
                           int n_kp_padded, float gamma_sq, int engine, int solver,
-                          float *partials, float *out_h, int *out_sweeps, void *stream) {
-  int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, engine, partials, stream);
+                          float *partials, int *tile_counters, float *out_h, int *out_sweeps, void *stream) {
+  if (!tile_counters || engine != APAP_GRAM_TCGEN05) {     // plain sequence: K2 starts when K1 has finished
+    int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, engine, partials, stream);
+    if (rc) return rc;
+    return apap_eig_denorm(partials, tmats, batch, cells, make_gram_plan(cells, n_kp_padded, engine).k_splits, solver,
+                           out_h, out_sweeps, stream);
+  }
+  int rc = check_table(kp_table, anchors, batch, cells, n_kp_padded);
   if (rc) return rc;
-  return apap_eig_denorm(partials, tmats, batch, cells, make_gram_plan(cells, n_kp_padded, engine).k_splits, solver, out_h,
-                         out_sweeps, stream);
+  if (!partials || !tmats || !out_h) return fail(APAP_E_BADARG, "null pointer");
+  if (solver != APAP_EIG_AUTO && solver != APAP_EIG_JACOBI) return fail(APAP_E_BADARG, "eig: unknown solver");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials, tile_counters, st);
+  if (rc) return rc;
+  return launch_eig(partials, tmats, batch, cells, make_gram_plan(cells, n_kp_padded, engine).k_splits, out_h, out_sweeps,
+                    solver == APAP_EIG_JACOBI, tile_counters, st);
 }
 
 int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,

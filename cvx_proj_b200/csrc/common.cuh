@@ -47,9 +47,9 @@ int check_cuda(cudaError_t e, const char *what);
 int launch_gram(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
                 float gamma_sq, float *partials, cudaStream_t st);
 int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded,
-                   float gamma_sq, float *partials, cudaStream_t st);
+                   float gamma_sq, float *partials, int *tile_done, cudaStream_t st);
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int k_splits,
-               float *out_h, int *out_sweeps, int force_jacobi, cudaStream_t st);
+               float *out_h, int *out_sweeps, int force_jacobi, int *tile_done, cudaStream_t st);
 int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
                   double gamma, double *out, cudaStream_t st);
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,

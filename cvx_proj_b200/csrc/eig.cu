@@ -37,7 +37,7 @@ __device__ __forceinline__ void combine_partials(const float *__restrict__ parti
   for (int s = 0; s < k_splits; ++s) {
     const float *src = partials + (size_t)s * kTerms * cells_padded + cell;
 #pragma unroll
-    for (int t = 0; t < kTerms; ++t) sum[t] += (double)__ldg(src + (size_t)t * cells_padded);
+    for (int t = 0; t < kTerms; ++t) sum[t] += (double)__ldcg(src + (size_t)t * cells_padded);   // L2: K1 may still be running
   }
 }
 
@@ -221,12 +221,27 @@ __device__ __forceinline__ void ldlt9_solve(const double (&a)[45], const double 
     for (int k = i + 1; k < 9; ++k) x[i] = fma(-a[tri(i, k)], x[k], x[i]);
 }
 
-__global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ partials,
-                                                      const double *__restrict__ tmats, int cells,
-                                                      int cells_padded, int k_splits, int force_jacobi,
-                                                      float *__restrict__ out_h, int *__restrict__ out_sweeps) {
+// 3 CTAs per SM (168 registers): a CTA fits beside two resident CTAs of K1, so in the overlapped launch K2
+// fills the SMs as K1's last CTAs retire.  tile_done (overlapped launch only): K1 counts the finished splits of
+// every 128-cell tile there; a CTA = one tile waits for its count, then clears it for the next call.
+__global__ void __launch_bounds__(kEigThreads, 3) k_eig(const float *partials, const double *__restrict__ tmats,
+                                                         int cells, int cells_padded, int k_splits, int force_jacobi,
+                                                         float *__restrict__ out_h, int *__restrict__ out_sweeps,
+                                                         int *tile_done) {
   const int cell = blockIdx.x * kEigThreads + threadIdx.x;
   const int scene = blockIdx.y;
+  if (tile_done) {
+    if (threadIdx.x == 0) {
+      int *cnt = tile_done + (size_t)scene * gridDim.x + blockIdx.x;
+      int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+        if (seen < k_splits) __nanosleep(200);
+      } while (seen < k_splits);
+      *cnt = 0;                                        // zero on exit: ready for the next call
+    }
+    __syncthreads();
+  }
   if (cell >= cells) return;
   partials += (size_t)scene * k_splits * kTerms * cells_padded;
   tmats += (size_t)scene * 18;
@@ -279,13 +294,30 @@ __global__ void __launch_bounds__(kEigThreads) k_eig(const float *__restrict__ p
 }
 
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int k_splits, float *out_h,
-               int *out_sweeps, int force_jacobi, cudaStream_t st) {
+               int *out_sweeps, int force_jacobi, int *tile_done, cudaStream_t st) {
   const int cells_padded = make_gram_plan(cells, kChunk, APAP_GRAM_FFMA2).cells_padded;   // depends on cells only
   dim3 grid((cells + kEigThreads - 1) / kEigThreads, batch);
   if (batch > 65535) return fail(APAP_E_TOOBIG, "eig: batch exceeds 65535");
-  k_eig<<<grid, kEigThreads, 0, st>>>(partials, tmats, cells, cells_padded, k_splits, force_jacobi, out_h,
-                                      out_sweeps);
-  return check_cuda(cudaGetLastError(), "k_eig launch");
+  if (!tile_done) {
+    k_eig<<<grid, kEigThreads, 0, st>>>(partials, tmats, cells, cells_padded, k_splits, force_jacobi, out_h, out_sweeps,
+                                        nullptr);
+    return check_cuda(cudaGetLastError(), "k_eig launch");
+  }
+  // overlapped with K1 (the previous kernel in the stream) by programmatic dependent launch: K2 may start once
+  // every CTA of K1 is running; it waits per tile on tile_done instead of on the completion of the grid
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kEigThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, k_eig, partials, tmats, cells, cells_padded, k_splits, force_jacobi, out_h,
+                                       out_sweeps, tile_done),
+                    "k_eig launch (programmatic dependent)");
 }
 
 }  // namespace apap

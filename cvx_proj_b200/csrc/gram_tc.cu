@@ -167,7 +167,7 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
 __device__ long long g_trace[4][160][4];           // [role][step][mark] SM clock of CTA (APAP_TC_TRACE, 0, 0)
 __device__ long long g_cta[8192][4];               // per CTA: SM id, globaltimer at entry, after the TMEM allocation, at exit
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define TRACE(role, step, mark) do { if (blockIdx.x == APAP_TC_TRACE && blockIdx.y == 0 && (step) < 160) g_trace[role][step][mark] = clock64(); } while (0)
+#define TRACE(role, step, mark) do { if (blockIdx.y == APAP_TC_TRACE && blockIdx.x == 0 && (step) < 160) g_trace[role][step][mark] = clock64(); } while (0)
 #else
 #define TRACE(role, step, mark) do { } while (0)
 #endif
@@ -196,11 +196,17 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
                                                                       const float *__restrict__ anchors, int cells,
                                                                       int cells_padded, int n_kb, int kb_per_split,
                                                                       int k_splits, float gamma_sq,
-                                                                      float *__restrict__ partials) {
+                                                                      float *__restrict__ partials,
+                                                                      int *__restrict__ tile_done) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem &sm = *reinterpret_cast<TcSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.y, scene = blockIdx.z;
+  // grid: x = split (fastest, so the CTAs of a tile run together and tiles complete progressively -- K2 can
+  // start on finished tiles while the last CTAs of K1 are still running), y = cell tile, z = scene
+  const int split = blockIdx.x, tile = blockIdx.y, scene = blockIdx.z;
+  // programmatic dependent launch: the next kernel in the stream (K2, when launched for overlap) may be
+  // scheduled once every CTA of this grid has got this far; it synchronises on tile_done, not on grid completion
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int kb0 = split * kb_per_split;
   const int nkb = min(n_kb, kb0 + kb_per_split) - kb0;            // k-blocks of this CTA: a multiple of kStageKb
   const int n_stage = nkb / kStageKb;
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
   partials += (size_t)scene * k_splits * kTerms * cells_padded;
 
 #ifdef APAP_TC_TRACE
-  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;   // launch order
   if (tid == 0 && cta_lin < 8192) {
     uint32_t smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
     g_cta[cta_lin][0] = smid; g_cta[cta_lin][1] = gtimer();
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
     // ================= producers: thread = cell of the tile = accumulator row = TMEM lane =====
     const int q = warp & 3, h = warp >> 2;         // lane quarter, step parity
     const int row = q * 32 + lane;                 // row of the tile
-    const int c = blockIdx.x * 128 + row;
+    const int c = tile * 128 + row;
     const float2 av = reinterpret_cast<const float2 *>(anchors)[min(c, cells - 1)];
     const float2 ax2 = make_float2(av.x, av.x), ay2 = make_float2(av.y, av.y);
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
       for (int t = 0; t < kTerms; ++t)
         if (t < nt) dst[(size_t)(t0 + t) * cells_padded] = sm.acc[t0 + t][row];
     }
+    __threadfence();                               // the partial sums are visible device-wide before the tile is counted
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer (one elected thread; the warp stays converged around it) ====
     const uint32_t idesc64 = idesc_tf32(2 * kNT), idesc32 = idesc_tf32(kNT);
@@ -411,24 +418,26 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
   __syncthreads();
   tc_fence_after();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+  // one more split of this tile is complete (release: every writer fenced before the barrier above)
+  if (tid == 0 && tile_done) atomicAdd(tile_done + (size_t)scene * gridDim.y + tile, 1);
 #ifdef APAP_TC_TRACE
   if (tid == 0 && cta_lin < 8192) g_cta[cta_lin][3] = gtimer();
 #endif
 }
 
 int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded, float gamma_sq,
-                   float *partials, cudaStream_t st) {
+                   float *partials, int *tile_done, cudaStream_t st) {
   const GramPlan p = make_gram_plan(cells, n_kp_padded, APAP_GRAM_TCGEN05);
   const int n_kb = n_kp_padded / kKB;
   const int kb_per_split = p.chunks_per_split * (kChunk / kKB);
-  dim3 grid((cells + 127) / 128, p.k_splits, batch);
-  if (p.k_splits > 65535 || batch > 65535) return fail(APAP_E_TOOBIG, "gram: grid.y/z exceeds 65535");
+  dim3 grid(p.k_splits, (cells + 127) / 128, batch);
+  if (grid.y > 65535 || batch > 65535) return fail(APAP_E_TOOBIG, "gram: more than 65535 cell tiles (8.3 M cells) or scenes per launch");
   if (APAP_TC_POLY > 0 && gamma_sq >= 0.25f)
     k_gram_tc<APAP_TC_POLY><<<grid, kTcThreads, sizeof(TcSmem), st>>>(kp_blocks, anchors, cells, p.cells_padded, n_kb,
-                                                                      kb_per_split, p.k_splits, gamma_sq, partials);
+                                                                      kb_per_split, p.k_splits, gamma_sq, partials, tile_done);
   else
     k_gram_tc<0><<<grid, kTcThreads, sizeof(TcSmem), st>>>(kp_blocks, anchors, cells, p.cells_padded, n_kb, kb_per_split,
-                                                           p.k_splits, gamma_sq, partials);
+                                                           p.k_splits, gamma_sq, partials, tile_done);
   return check_cuda(cudaGetLastError(), "k_gram_tc launch");
 }
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 5
+#define APAP_ABI_VERSION 6
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -100,10 +100,17 @@ int apap_gram_partials(const float *kp_table, const float *anchors, int batch, i
 int apap_eig_denorm(const float *partials, const double *tmats, int batch, int cells,
                     int k_splits, int solver, float *out_h, int *out_sweeps, void *stream);
 
-/* K1 + K2 back to back on `stream` (what APAP.local_homography calls). */
+/*
+ * K1 + K2 on `stream` (what APAP.local_homography calls).
+ *   tile_counters : optional int32 [batch][ceil(cells / 128)] scratch, ALL ZERO on entry and all zero again when the
+ *                   call has completed.  When given (engine TCGEN05), K2 is launched as a programmatic dependent of
+ *                   K1: K1 counts the finished keypoint splits of every 128-cell tile there and K2's CTAs start on
+ *                   finished tiles while K1's last CTAs are still running, instead of after the whole grid.
+ *                   NULL = K2 starts when K1 has finished.
+ */
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats,
                           int batch, int cells, int n_kp_padded, float gamma_sq, int engine, int solver,
-                          float *partials, float *out_h, int *out_sweeps, void *stream);
+                          float *partials, int *tile_counters, float *out_h, int *out_sweeps, void *stream);
 
 /*
  * Second output of APAP.local_homography (pyviz/apap.py:144,153): float64 weights

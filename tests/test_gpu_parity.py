@@ -161,6 +161,26 @@ def test_cell_row_sharding_is_bitwise_identical(engine):
         assert np.array_equal(part, full[r0:r1])
 
 
+def test_overlapped_k2_launch_equals_plain_sequence():
+    """K2 launched as a programmatic dependent of K1 (per-tile completion counters) gives the same bits as the
+    plain K1 -> K2 sequence, call after call (the counters are zero again after every call), batches included."""
+    import torch
+    from cvx_proj_b200.apap import scale_anchors, weight_scale
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for name, kw, batch in (("c1", {}, 1), ("mini", {"n_kp": 3000, "mesh": 50}, 3), ("c2", {}, 1)):
+        sc = synth.make_scene(name, **kw)
+        st = _stitcher(sc)
+        table, tmats = st._prepare(sc.src, sc.dst)
+        t = st.kp_table_device(torch.from_numpy(np.stack([table] * batch)).to(dev))
+        a = torch.from_numpy(np.stack([scale_anchors(sc.vertices, weight_scale(sc.sigma))] * batch)).to(dev)
+        m = torch.from_numpy(np.stack([tmats] * batch)).to(dev)
+        plain = st.local_homography_device(t, a, m, batch, sc.n_cells, overlap=False).cpu().numpy()
+        for _ in range(4):
+            got = st.local_homography_device(t, a, m, batch, sc.n_cells, overlap=True).cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), plain.view(np.uint32))
+        assert int(st._tile_counters(torch, dev, batch, sc.n_cells).abs().sum().item()) == 0
+
+
 def test_gram_engines_agree_on_partial_sums():
     """The tensor-core (3xTF32, TMEM) and the FP32 SIMT Gram kernels produce the same partial sums to
     ~1e-6 of the largest sum of each term (tcgen05 accumulates per 256-keypoint segment)."""
