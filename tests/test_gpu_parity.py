@@ -345,6 +345,68 @@ def test_local_warp_c2_full_size_vs_oracle():
     assert diff.size == 0, f"{diff.size} pixels differ, first {diff[:5]}"
 
 
+def _sampled_cells_vs_oracle(sc, h, step):
+    """H grid on every `step`-th cell row / column against the float64 Gram oracle (the full grid is too much
+    float64 work for the CPU at the BASELINE sizes; the GPU computed every cell)."""
+    ref = orc.local_homography_gram64(sc.src, sc.dst, np.ascontiguousarray(sc.vertices[::step, ::step]), sc.gamma,
+                                      sc.sigma)
+    return _herr(np.ascontiguousarray(h[::step, ::step]), ref, sc)
+
+
+def test_c3_full_size_grid_and_warp():
+    """BASELINE config c3 at full size on one GPU: 8K pair, 20 000 keypoints, 400 x 400 grid, 41.5 Mpix canvas."""
+    sc = synth.make_scene("c3")
+    st = _stitcher(sc)
+    h, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    assert h.shape == (400, 400, 3, 3) and np.isfinite(h).all() and np.all(h[..., 2, 2] == 1.0)
+    err = _sampled_cells_vs_oracle(sc, h, 40)
+    print(f"c3 sampled cells: normalised H error max {err.max():.3e}")
+    assert err.max() <= H_GATE
+    img = sc.image(1)
+    inv = orc.invert_grid(h)
+    want = orc.local_warp(img, inv, sc.mesh, (sc.final_w, sc.final_h), (sc.offset_x, sc.offset_y))
+    grid = h.copy()
+    got = st.local_warp(img, grid, sc.mesh)
+    assert np.array_equal(grid, inv)                                   # in-place inverse, the reference's bits
+    diff = np.flatnonzero((got != want).any(axis=-1).ravel())
+    assert diff.size == 0, f"{diff.size} pixels differ, first {diff[:5]}"
+    # idempotence of the pipeline on its own output grid, and the row bands of a 4-way shard tile the canvas
+    col, row = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, 400, 400)
+    shards = sharding.plan_shards(row, 400, 4)
+    assert shards[0].px_row0 == 0 and shards[-1].px_row1 == sc.final_h
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    src_dev = torch.from_numpy(img).to(dev)
+    for s in shards:
+        tabs = st.warp_tables_device(inv, col, row, sc.width, sc.height, dev, s.px_row0, s.px_row1)
+        band = st.warp_device(src_dev, tabs, 400).cpu().numpy()
+        assert np.array_equal(band, want[s.px_row0:s.px_row1])
+
+
+def test_c5_keypoint_sweep_ends_vs_oracle():
+    """BASELINE config c5 (256 x 256 grid) at both ends of the keypoint sweep, 1k and 64k."""
+    for n_kp in (1000, 64000):
+        sc = synth.make_scene("c5", n_kp=n_kp)
+        h, _ = _stitcher(sc).local_homography(sc.src, sc.dst, sc.vertices)
+        err = _sampled_cells_vs_oracle(sc, h, 32)
+        print(f"c5 N={n_kp}: normalised H error max {err.max():.3e}")
+        assert np.isfinite(h).all() and err.max() <= H_GATE
+
+
+def test_c4_batch_of_64_pairs():
+    """BASELINE config c4: 64 1080p pairs (2 000 keypoints, 100 x 100 grid) in one launch; every pair equals its
+    single-pair call bit for bit, sampled cells match the oracle."""
+    scs = [synth.make_scene("c4", seed=k) for k in range(64)]
+    st = _stitcher(scs[0])
+    hs = st.local_homography_batch([sc.src for sc in scs], [sc.dst for sc in scs], [sc.vertices for sc in scs])
+    assert len(hs) == 64
+    for k in (0, 17, 63):
+        single, _ = st.local_homography(scs[k].src, scs[k].dst, scs[k].vertices)
+        assert np.array_equal(hs[k].view(np.uint32), single.view(np.uint32))
+        assert _sampled_cells_vs_oracle(scs[k], hs[k], 20).max() <= H_GATE
+    assert all(np.isfinite(x).all() for x in hs)
+
+
 def test_identity_and_translation_hit_exact_integers():
     """Integer-valued coordinates sit exactly on the truncation boundary: every pixel is decided
     by the float64 path and must match the reference rule (strict bounds drop row/column 0)."""
