@@ -356,7 +356,11 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
   p.chunks_per_row = (canvas_w + 31) / 32;
   p.src_h = src_h; p.src_w = src_w; p.grid_cols = grid_cols; p.canvas_w = canvas_w;
   p.off_x = off_x; p.off_y = off_y; p.centre_h = centre_h; p.centre_w = centre_w; p.force_exact = force_exact;
+#ifdef APAP_WARP_NOWORDS
+  const bool words = false;                        // lab: byte stores always
+#else
   const bool words = (canvas_w % 4 == 0) && !(reinterpret_cast<uintptr_t>(out_band) & 3u);
+#endif
   // one resident wave: grid.x CTAs side by side cover the canvas width, grid.y of them share its height
   const int gx = (p.chunks_per_row + kWarpsPerCta - 1) / kWarpsPerCta;
   const int visits = (n_blocks + 1) / 2;           // a visit = two consecutive row blocks

@@ -1,2 +1,7 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "c3_full or c5_keypoint or c4_batch" -s 2>&1 | tail -12
-timeout 900 python -m pytest tests -m gpu -x -q --durations=5 2>&1 | tail -12
+N=${1:-4}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?"; tail -3 gpurun_out/bench_${N}gpu.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","n_gpus","ms_per_step","scaling")}); print(json.dumps(d.get("c3_sharded")))
+PY
