@@ -29,6 +29,12 @@
 
 namespace apap {
 
+#ifndef APAP_WARP_PIPELINE
+#define APAP_WARP_PIPELINE 0     // 1: the gathers of both blocks of a visit in flight before the first is stored
+#endif
+#ifndef APAP_WARP_CTAS
+#define APAP_WARP_CTAS 4         // resident CTAs per SM the kernel is compiled for (register cap 64 / 85 / 128)
+#endif
 constexpr int kWarpThreads = 256;
 constexpr int kWarpsPerCta = kWarpThreads / 32;
 constexpr int kBlockRows = APAP_WARP_BLOCK_ROWS;      // rows per row block (processed as 2 pairs)
@@ -216,7 +222,7 @@ __device__ __forceinline__ void prefetch_l1(const void *ptr) {
 // column state stays loop invariant.  The cell record of the next visit is prefetched into L1
 // while the current visit's gathers are in flight.
 template <bool kBlend, bool kWords>
-__global__ void __launch_bounds__(kWarpThreads, 4) k_warp(const WarpParams p) {
+__global__ void __launch_bounds__(kWarpThreads, APAP_WARP_CTAS) k_warp(const WarpParams p) {
   const int lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (chunk >= p.chunks_per_row) return;           // warp-uniform
@@ -264,10 +270,19 @@ __global__ void __launch_bounds__(kWarpThreads, 4) k_warp(const WarpParams p) {
         prefetch_l1(rec);
         prefetch_l1(rec + 32);
       }
+#if APAP_WARP_PIPELINE
+      // both blocks' gathers in flight before the first block is packed and stored
+      uint32_t b0[kBlockRows], b1[kBlockRows], b2[kBlockRows], cb0[kBlockRows], cb1[kBlockRows], cb2[kBlockRows];
+      enter_cell_row(p, cl, dxf, (int)(cur1.y & 0xffffu), c);
+      block_issue<kBlend, true>(p, src, i0b, nb, (float)(cur1.y >> 16), x, col_ok, c, b0, b1, b2, cb0, cb1, cb2);
+      block_store<kBlend, kWords, true>(p, i0a, na, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+      block_store<kBlend, kWords, true>(p, i0b, nb, b0, b1, b2, cb0, cb1, cb2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+#else
       block_store<kBlend, kWords, true>(p, i0a, na, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
       enter_cell_row(p, cl, dxf, (int)(cur1.y & 0xffffu), c);
       block_issue<kBlend, true>(p, src, i0b, nb, (float)(cur1.y >> 16), x, col_ok, c, a0, a1, a2, ca0, ca1, ca2);
       block_store<kBlend, kWords, true>(p, i0b, nb, a0, a1, a2, ca0, ca1, ca2, lane_off, pitch, lane_a, lane_b, sel, store_ok);
+#endif
     } else {                                       // partial blocks (cell rows shorter than 4 canvas rows, band end)
       enter_cell_row(p, cl, dxf, (int)(cur0.y & 0xffffu), c);
       block_issue<kBlend, false>(p, src, i0a, na, (float)(cur0.y >> 16), x, col_ok, c, a0, a1, a2, ca0, ca1, ca2);
@@ -364,7 +379,7 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
   // one resident wave: grid.x CTAs side by side cover the canvas width, grid.y of them share its height
   const int gx = (p.chunks_per_row + kWarpsPerCta - 1) / kWarpsPerCta;
   const int visits = (n_blocks + 1) / 2;           // a visit = two consecutive row blocks
-  int gy = (sm_count_cached() * 4) / gx;           // 4 CTAs of 8 warps resident per SM (launch bounds)
+  int gy = (sm_count_cached() * APAP_WARP_CTAS) / gx;   // APAP_WARP_CTAS CTAs of 8 warps resident per SM (launch bounds)
   if (gy < 1) gy = 1;
   if (gy > visits) gy = visits;
   if (gy > 65535) gy = 65535;

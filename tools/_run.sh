@@ -1,7 +1,4 @@
-N=${1:-4}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?"; tail -3 gpurun_out/bench_${N}gpu.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ("value","n_gpus","ms_per_step","scaling")}); print(json.dumps(d.get("c3_sharded")))
-PY
+timeout 120 python tools/time_kernels.py c2 10 warp,fused
+for v in p1c4 p1c3 p0c3 p1c2; do APAP_B200_LIB=cvx_proj_b200/lab/$v.so timeout 120 python tools/time_kernels.py c2 10 warp,fused; done
+timeout 120 python tools/time_kernels.py c3 5 warp,fused
+for v in p1c4 p1c3 p0c3 p1c2; do APAP_B200_LIB=cvx_proj_b200/lab/$v.so timeout 120 python tools/time_kernels.py c3 5 warp,fused; done
