@@ -17,6 +17,10 @@ p = bench.Pass(torch, dev, name)
 p.gram(); p.eig()
 p.prepare_warp()
 for _ in range(iters):
-    p.gram(); p.eig(); p.warp(False); p.warp(True); p.blend()
+    p.gram(); p.eig()                                   # K1, K2 one by one
+    p.dlt()                                             # K1 + K2 as the public call launches them (K2 overlapped)
+    p.st.kp_table_device(p.rows)                        # k_kp_blocks
+    p.prepare_warp()                                    # k_warp_prep (+ uploads)
+    p.warp(False); p.warp(True); p.blend()
 torch.cuda.synchronize()
 print("profile pass ok", name, iters)
