@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 6
+#define APAP_ABI_VERSION 7
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -177,6 +177,21 @@ int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, vo
 int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream);
 int apap_warp_tables(const float *cell_hinv, const int *col_extent, const int *row_extent, int grid_rows,
                      int grid_cols, int off_x, int off_y, int src_w, int src_h, float *cell_fast, void *stream);
+
+/*
+ * Global-homography warp of the reference's README pipeline: `image_warping`,
+ * pyviz/utils.py:93-127 = cv.warpPerspective(img2warp, Ht.H, canvas) (bilinear, constant border 0) followed by the
+ * base image pasted over the canvas (:124-125) or the mean-blend loop (:115-123).  Bit-exact with OpenCV's 8-bit
+ * fixed-point bilinear warp (coordinates in 1/32 pixel, 15-bit weights).
+ *   inverse_map : double [9] HOST memory, row-major: canvas (x, y, 1) -> source pixel, i.e. cv::invert(Ht.H)
+ *   dst         : uint8 [dst_h][dst_w][3] canvas (device), every pixel written
+ *   base        : optional uint8 [base_h][base_w][3] (device) placed at (off_x, off_y) on the canvas
+ *   mode        : 0 warp only; 1 paste the base over the warp (direct_blend=True); 2 mean blend: inside the base
+ *                 rectangle (warp + base) >> 1 where any channel of the warp is non-zero, else the base pixel
+ */
+int apap_warp_perspective(const uint8_t *src, int src_h, int src_w, const double *inverse_map, uint8_t *dst,
+                          int dst_h, int dst_w, const uint8_t *base, int base_h, int base_w, int off_x, int off_y,
+                          int mode, void *stream);
 
 /*
  * Pipe probes for the roofline denominators that MEASURED_PEAKS.json does not hold.  Runs `iters` x 16

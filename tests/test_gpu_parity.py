@@ -525,6 +525,44 @@ def test_stitch_pair_driver_vs_oracle_pipeline():
     assert np.array_equal(res.stitched, want)
 
 
+# ------------------------------------------------------------- global-homography warp
+def test_image_warping_bit_exact_vs_reference_golden(golden):
+    """cvx_proj_b200.utils.image_warping against the live reference's outputs (cv.warpPerspective + paste / mean
+    blend, pyviz/utils.py:93-127): every case, both modes, bit-exact."""
+    from cvx_proj_b200 import utils as putils
+    from oracle.gen_golden_warping import CASES, FULL, warping_case
+    g = golden("ref_image_warping.npz")
+    for name in CASES:
+        base, warp, hmat = warping_case(name)
+        for db in (True, False):
+            tag = f"{name}_{'paste' if db else 'mean'}"
+            res = putils.image_warping(base, warp, hmat, direct_blend=db)
+            assert res.dtype == np.uint8 and tuple(g[tag + "_shape"]) == res.shape
+            crc = np.array([zlib.crc32(np.ascontiguousarray(r).tobytes()) for r in res], dtype=np.uint32)
+            bad = np.flatnonzero(crc != g[tag + "_rowcrc"])
+            assert bad.size == 0, (tag, bad[:8])
+            if name in FULL:
+                assert np.array_equal(res, g[tag])
+
+
+def test_warp_perspective_4k_and_degenerate_maps_vs_oracle():
+    from cvx_proj_b200 import utils as putils
+    from oracle import warp_oracle as wo
+    img = synth.make_image(3840, 2160, seed=1)
+    hmat = synth.ground_truth_h(3840, 2160)
+    cw, ch, tx, ty, m = putils.warping_canvas(img.shape, img.shape, hmat)
+    got = putils.warp_perspective(img, m, (cw, ch))
+    want = wo.warp_perspective(img, m, (cw, ch))
+    diff = np.flatnonzero((got != want).any(axis=-1).ravel())
+    assert diff.size == 0, f"{diff.size} pixels differ, first {diff[:5]}"
+    small = synth.make_image(200, 100, seed=9)
+    for mm in (np.eye(3), np.array([[1, 0, 0.5], [0, 1, 0.25], [0, 0, 1.0]]), np.array([[1, 0, 0], [0, 1, 0], [0.01, 0, 1.0]]),
+               np.array([[0.5, 0.2, -300], [0.1, 2, 50], [-0.002, 0.001, 1.0]]), np.zeros((3, 3)),
+               np.array([[1e-9, 0, 0], [0, 1e-9, 0], [0, 0, 1.0]])):
+        assert np.array_equal(putils.warp_perspective(small, mm, (300, 200)), wo.warp_perspective(small, mm, (300, 200)))
+    assert putils.warp_perspective(small, np.eye(3), (7, 3)).shape == (3, 7, 3)
+
+
 def test_errors_surface_as_exceptions():
     st = APAP(0.5, 100, [64, 48], [0, 0])
     with pytest.raises(ValueError):

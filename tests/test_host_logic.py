@@ -297,7 +297,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 6
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 7
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 
@@ -386,3 +386,20 @@ def test_mat_layout_bit_exact_vs_reference_and_in_place(golden, name, tmp_path):
     path = driver.save2mat("H31_apap", mat, name="H", prefix=str(tmp_path) + "/")
     back = scipy.io.loadmat(path)
     assert np.array_equal(back["H"], mat)
+
+
+def test_image_warping_host_arithmetic(golden):
+    """Canvas size / offsets / composed matrix and the closed-form inverse of cvx_proj_b200.utils against the
+    golden canvases' shapes (live reference) and the oracle."""
+    from cvx_proj_b200 import utils as putils
+    from oracle import warp_oracle as wo
+    from oracle.gen_golden_warping import CASES, warping_case
+    g = golden("ref_image_warping.npz")
+    for name in CASES:
+        base, warp, hmat = warping_case(name)
+        cw, ch, tx, ty, m = putils.warping_canvas(base.shape, warp.shape, hmat)
+        assert (ch, cw, 3) == tuple(g[name + "_paste_shape"])
+        ow = wo.warping_canvas(base.shape, warp.shape, hmat)
+        assert (cw, ch, tx, ty) == ow[:4] and np.array_equal(m, ow[4])
+        assert np.array_equal(putils.invert3x3(m).view(np.uint64), wo.invert3x3(m).view(np.uint64))
+    assert np.array_equal(putils.invert3x3(np.zeros((3, 3))), np.zeros((3, 3)))

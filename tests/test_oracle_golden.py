@@ -125,3 +125,23 @@ def test_blend_edge_cases(golden):
     g = golden("ref_blend.npz")
     assert np.array_equal(orc.uniform_blend(g["a"], g["b"]), g["out"])
     assert np.array_equal(orc.uniform_blend_float(g["a"], g["b"]), g["out"])
+
+
+# ------------------------------------------------------------- global-homography warp
+def test_image_warping_oracle_reproduces_live_reference(golden):
+    """oracle/warp_oracle.py (OpenCV's fixed-point bilinear warp restated) against outputs of the live reference's
+    utils.image_warping (oracle/gen_golden_warping.py), both blend modes, odd sizes."""
+    import hashlib
+    from oracle import warp_oracle as wo
+    from oracle.gen_golden_warping import CASES, FULL, warping_case
+    g = golden("ref_image_warping.npz")
+    for name in CASES:
+        base, warp, hmat = warping_case(name)
+        assert np.array_equal(hmat, g[name + "_H"])
+        for db in (True, False):
+            tag = f"{name}_{'paste' if db else 'mean'}"
+            res = wo.image_warping(base, warp, hmat, direct_blend=db)
+            assert tuple(g[tag + "_shape"]) == res.shape
+            assert hashlib.sha256(res.tobytes()).hexdigest() == str(g[tag + "_sha"]), tag
+            if name in FULL:
+                assert np.array_equal(res, g[tag])

@@ -1,4 +1,3 @@
-timeout 120 python tools/time_kernels.py c2 10 warp,fused
-for v in p1c4 p1c3 p0c3 p1c2; do APAP_B200_LIB=cvx_proj_b200/lab/$v.so timeout 120 python tools/time_kernels.py c2 10 warp,fused; done
-timeout 120 python tools/time_kernels.py c3 5 warp,fused
-for v in p1c4 p1c3 p0c3 p1c2; do APAP_B200_LIB=cvx_proj_b200/lab/$v.so timeout 120 python tools/time_kernels.py c3 5 warp,fused; done
+timeout 600 python -m pytest tests -m gpu -x -q -k "image_warping or warp_perspective" 2>&1 | tail -5
+timeout 120 python tools/time_kernels.py c2 10 gwarp,gwarp_paste,gwarp_mean,warp
+timeout 120 python tools/time_kernels.py c3 5 gwarp,gwarp_paste,gwarp_mean

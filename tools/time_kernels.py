@@ -23,12 +23,24 @@ flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
 p.gram(); p.eig()
 if any(w in what for w in ("warp", "fused", "blend")):
     p.prepare_warp()
-ops = {"gram": p.gram, "eig": p.eig, "warp": lambda: p.warp(False), "fused": lambda: p.warp(True), "blend": p.blend}
+def _gwarp_setup():
+    from cvx_proj_b200 import utils as putils, synth as _synth
+    sc = p.sc
+    img = torch.from_numpy(sc.image(1)).to(dev)
+    base = torch.from_numpy(_synth.make_image(sc.width, sc.height, seed=2)).to(dev)
+    cw, ch, tx, ty, m = putils.warping_canvas(img.shape, img.shape, sc.h_gt)
+    out = torch.empty((ch, cw, 3), dtype=torch.uint8, device=dev)
+    return lambda mode: putils.warp_perspective(img, m, (cw, ch), base=base, offset=(tx, ty), mode=mode, out=out)
+
+
+_gw = _gwarp_setup() if any(w.startswith("gwarp") for w in what) else None
+ops = {"gwarp": lambda: _gw(0), "gwarp_paste": lambda: _gw(1), "gwarp_mean": lambda: _gw(2), "gram": p.gram, "eig": p.eig, "warp": lambda: p.warp(False), "fused": lambda: p.warp(True), "blend": p.blend}
 res = {}
 for w in what:
     ts = []
     for k in range(iters + 3):
-        flush.add_(1)
+        if not os.environ.get('NOFLUSH'):
+            flush.add_(1)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); ops[w](); e1.record(); e1.synchronize()
         if k >= 3:
