@@ -16,11 +16,22 @@ dev = torch.device("cuda", 0)
 p = bench.Pass(torch, dev, name)
 p.gram(); p.eig()
 p.prepare_warp()
+from cvx_proj_b200 import utils as putils  # noqa: E402
+
+g_cw, g_ch, g_tx, g_ty, g_m = putils.warping_canvas(p.host_img.shape, p.host_img.shape, p.sc.h_gt)
+g_out = torch.empty((g_ch, g_cw, 3), dtype=torch.uint8, device=dev)
+
+
+def gw(mode):
+    putils.warp_perspective(p.img, g_m, (g_cw, g_ch), base=p.centre, offset=(g_tx, g_ty), mode=mode, out=g_out)
+
+
 for _ in range(iters):
     p.gram(); p.eig()                                   # K1, K2 one by one
     p.dlt()                                             # K1 + K2 as the public call launches them (K2 overlapped)
     p.st.kp_table_device(p.rows)                        # k_kp_blocks
     p.prepare_warp()                                    # k_warp_prep (+ uploads)
     p.warp(False); p.warp(True); p.blend()
+    gw(0); gw(1); gw(2)                                 # k_warp_global: warp only, paste, mean blend
 torch.cuda.synchronize()
 print("profile pass ok", name, iters)
