@@ -737,6 +737,16 @@ class APAP:
         """
         return self._warp(ori_img, local_homography, mesh)
 
+    def local_warp_batch(self, ori_imgs, local_homographies, mesh, centre_imgs=None):
+        """Extension (no reference API; its multi-image mode is a shell loop, run_all.sh:15,29): ``local_warp`` --
+        or ``local_warp_blend`` when ``centre_imgs`` is given -- for several pairs that share the canvas and the
+        mesh.  Every grid is inverted in place like the single call; each item equals the single-pair call."""
+        centres = centre_imgs if centre_imgs is not None else [None] * len(ori_imgs)
+        if not (len(ori_imgs) == len(local_homographies) == len(centres)):
+            raise ValueError("local_warp_batch: one image, one grid (and one centre image) per pair")
+        return [self._warp(img, grid, mesh, centre_img=centre) for img, grid, centre in
+                zip(ori_imgs, local_homographies, centres)]
+
     def local_warp_blend(self, ori_img, local_homography, mesh, centre_img):
         """Extension: the reference driver's commented pipeline (pyviz/apap.py:258-261) in one
         kernel -- warp, paste ``centre_img`` at the offsets, ``uniform_blend``.  Same in-place

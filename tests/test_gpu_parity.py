@@ -407,6 +407,23 @@ def test_c4_batch_of_64_pairs():
     assert all(np.isfinite(x).all() for x in hs)
 
 
+def test_local_warp_batch_equals_single_calls():
+    scs = [synth.make_scene("mini", seed=k) for k in range(3)]
+    st = _stitcher(scs[0])
+    hs = st.local_homography_batch([sc.src for sc in scs], [sc.dst for sc in scs], scs[0].vertices)
+    imgs = [sc.image(10 + k) for k, sc in enumerate(scs)]
+    centres = [synth.make_image(scs[0].width, scs[0].height, seed=20 + k) for k in range(3)]
+    grids = [h.copy() for h in hs]
+    out = st.local_warp_batch(imgs, grids, scs[0].mesh)
+    fused = st.local_warp_batch(imgs, [h.copy() for h in hs], scs[0].mesh, centres)
+    for k in range(3):
+        g = hs[k].copy()
+        assert np.array_equal(out[k], st.local_warp(imgs[k], g, scs[0].mesh)) and np.array_equal(grids[k], g)
+        assert np.array_equal(fused[k], st.local_warp_blend(imgs[k], hs[k].copy(), scs[0].mesh, centres[k]))
+    with pytest.raises(ValueError):
+        st.local_warp_batch(imgs, grids[:2], scs[0].mesh)
+
+
 def test_identity_and_translation_hit_exact_integers():
     """Integer-valued coordinates sit exactly on the truncation boundary: every pixel is decided
     by the float64 path and must match the reference rule (strict bounds drop row/column 0)."""

@@ -1,3 +1,2 @@
-which compute-sanitizer
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "tiny or mini or ragged or clamp or overlapped or device_kp or device_warp or image_warping or degenerate or tiny_and_ragged or row_bands or blend_golden or batch_equals" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -6 gpurun_out/sanitizer_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "(golden and tiny) or image_warping or overlapped" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -6 gpurun_out/sanitizer_racecheck.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/check_sharded_nccl.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tee gpurun_out/sharded_nccl_check.txt
+timeout 300 python -m pytest tests -m gpu -x -q -k "warp_batch" 2>&1 | tail -3
