@@ -18,7 +18,6 @@ CUDA ``torch`` tensor as the image keeps the result on the device (opt-in).
 """
 from __future__ import annotations
 
-import ctypes
 import math
 import os
 from concurrent.futures import ThreadPoolExecutor

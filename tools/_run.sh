@@ -1,2 +1,3 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/check_sharded_nccl.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tee gpurun_out/sharded_nccl_check.txt
-timeout 300 python -m pytest tests -m gpu -x -q -k "warp_batch" 2>&1 | tail -3
+timeout 600 python -m pytest tests -m gpu -x -q -k "image_warping or warp_perspective" 2>&1 | tail -5
+timeout 120 python tools/time_kernels.py c2 10 gwarp,gwarp_paste,gwarp_mean,warp
+timeout 120 python tools/time_kernels.py c3 5 gwarp,gwarp_paste,gwarp_mean
