@@ -601,14 +601,19 @@ class APAP:
             partials = torch.empty(batch * nbytes // 4, dtype=torch.float32, device=device)
         if out_h is None:
             out_h = torch.empty((batch, cells, 9), dtype=torch.float32, device=device)
-        with torch.cuda.device(device):
-            rt.check(lib.apap_local_homography(
-                table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
-                float(np.float32(float(self.gamma) ** 2)), engine, int(solver), partials.data_ptr(),
-                self._tile_counters(torch, device, batch, cells).data_ptr()
-                if overlap and engine == rt.GRAM_TCGEN05 else None, out_h.data_ptr(),
-                sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
-                "apap_local_homography")
+        counters = (self._tile_counters(torch, device, batch, cells)
+                    if overlap and engine == rt.GRAM_TCGEN05 else None)
+        try:
+            with torch.cuda.device(device):
+                rt.check(lib.apap_local_homography(
+                    table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
+                    float(np.float32(float(self.gamma) ** 2)), engine, int(solver), partials.data_ptr(),
+                    counters.data_ptr() if counters is not None else None, out_h.data_ptr(),
+                    sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
+                    "apap_local_homography")
+        except Exception:
+            self._counters = None          # a failed call may leave counts behind: never reuse that scratch
+            raise
         return out_h
 
     def local_homography(self, src_point, dst_point, vertices):

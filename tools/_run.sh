@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "image_warping or warp_perspective" 2>&1 | tail -5
-timeout 120 python tools/time_kernels.py c2 10 gwarp,gwarp_paste,gwarp_mean,warp
-timeout 120 python tools/time_kernels.py c3 5 gwarp,gwarp_paste,gwarp_mean
+timeout 120 python tools/time_kernels.py c2 10 gram
+for v in poly1 poly3 poly4; do APAP_B200_LIB=cvx_proj_b200/lab/$v.so timeout 120 python tools/time_kernels.py c2 10 gram; done
+timeout 120 python tools/time_kernels.py c3 5 gram
+for v in poly1 poly3; do APAP_B200_LIB=cvx_proj_b200/lab/$v.so timeout 120 python tools/time_kernels.py c3 5 gram; done
