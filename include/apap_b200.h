@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 7
+#define APAP_ABI_VERSION 8
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -192,6 +192,21 @@ int apap_warp_tables(const float *cell_hinv, const int *col_extent, const int *r
 int apap_warp_perspective(const uint8_t *src, int src_h, int src_w, const double *inverse_map, uint8_t *dst,
                           int dst_h, int dst_w, const uint8_t *base, int base_h, int base_w, int off_x, int off_y,
                           int mode, void *stream);
+
+/*
+ * Spectral match weighting of the reference's README pipeline: calculate_M,
+ * pyviz/spectral_method.py:96-125.
+ * apap_affinity_matrix: M [n][n] float64 (device): M[i][i] = diag[i] (match score + epipolar term, :104-111, computed
+ *   by the caller), M[i][j] = max(4.5 - ((|s_i - s_j|^2 - |d_i - d_j|^2)^2) * rcp_value, 0) in numpy's float32
+ *   arithmetic (:112-118); src_pts / dst_pts: float [n][2] (device), rcp_value = 1 / (2 affinity_eps^2).
+ * apap_power_step: one step of the power iteration that replaces np.linalg.svd(M) + |U[:, 0]| (:122-123):
+ *   y = M x, x <- y / |y|; *max_diff_bits is raised (atomic max on the bits of a non-negative double) to
+ *   max_i |x_new[i] - x_old[i]|, for the caller's convergence test.  x, y: double [n]; norm_sq: double [1] scratch.
+ */
+int apap_affinity_matrix(const float *src_pts, const float *dst_pts, const double *diag, int n, float rcp_value,
+                         double *m, void *stream);
+int apap_power_step(const double *m, int n, double *x, double *y, double *norm_sq,
+                    unsigned long long *max_diff_bits, void *stream);
 
 /*
  * Pipe probes for the roofline denominators that MEASURED_PEAKS.json does not hold.  Runs `iters` x 16

@@ -580,6 +580,44 @@ def test_warp_perspective_4k_and_degenerate_maps_vs_oracle():
     assert putils.warp_perspective(small, np.eye(3), (7, 3)).shape == (3, 7, 3)
 
 
+# ------------------------------------------------------------- spectral match weighting
+def test_calculate_m_vs_reference_golden(golden):
+    """cvx_proj_b200.spectral_method.calculate_M against the live reference's outputs: the affinity matrix is the
+    reference's bit for bit (checked through the oracle), the leading singular vector within 1e-10 of numpy's SVD,
+    the masks identical."""
+    import torch
+    from types import SimpleNamespace
+    from cvx_proj_b200 import spectral_method as psm
+    from oracle import spectral_oracle as so
+    from oracle.gen_golden_spectral import CASES, OPTS, spectral_case
+    g = golden("ref_spectral.npz")
+    opts = SimpleNamespace(**OPTS)
+    lib = rt.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for name in CASES:
+        c, o, cf, of, fmat, hg = spectral_case(name)
+        n = c.shape[0]
+        kc = [SimpleNamespace(pt=(float(x), float(y))) for x, y in c]
+        ko = [SimpleNamespace(pt=(float(x), float(y))) for x, y in o]
+        matches = [SimpleNamespace(queryIdx=i, trainIdx=i) for i in range(n)]
+        seg, h_ret, rmask, omask = psm.calculate_M(kc, cf.copy(), ko, of.copy(), fmat, matches, opts, Hg=hg)
+        assert h_ret is hg and seg.dtype == np.float64 and rmask.dtype == np.float32
+        err = np.abs(seg - g[name + "_segment"]).max()
+        print(f"{name}: max |segment - reference| = {err:.2e}")
+        assert err <= 1e-10
+        assert np.array_equal(omask, g[name + "_original_mask"])
+        assert np.allclose(rmask, g[name + "_ransac_mask"], rtol=0, atol=1e-7)
+        if n <= 1000:                                  # the matrix itself, bit for bit
+            diag = psm.affinity_diagonal(c, o, cf, of, fmat, OPTS["epi_weight"])
+            m = torch.empty((n, n), dtype=torch.float64, device=dev)
+            c_dev, o_dev, g_dev = (torch.from_numpy(v).to(dev) for v in (c, o, diag))       # keep them alive
+            rt.check(lib.apap_affinity_matrix(c_dev.data_ptr(), o_dev.data_ptr(), g_dev.data_ptr(), n,
+                                              float(np.float32(1 / 2 / OPTS["affinity_eps"] ** 2)), m.data_ptr(),
+                                              rt.stream_ptr(torch, dev)), "affinity")
+            want = so.affinity_matrix(c, o, cf, of, fmat, OPTS["epi_weight"], OPTS["affinity_eps"])
+            assert np.array_equal(m.cpu().numpy(), want)
+
+
 def test_errors_surface_as_exceptions():
     st = APAP(0.5, 100, [64, 48], [0, 0])
     with pytest.raises(ValueError):

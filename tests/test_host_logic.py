@@ -297,7 +297,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 7
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 8
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 
@@ -403,3 +403,29 @@ def test_image_warping_host_arithmetic(golden):
         assert (cw, ch, tx, ty) == ow[:4] and np.array_equal(m, ow[4])
         assert np.array_equal(putils.invert3x3(m).view(np.uint64), wo.invert3x3(m).view(np.uint64))
     assert np.array_equal(putils.invert3x3(np.zeros((3, 3))), np.zeros((3, 3)))
+
+
+def test_spectral_host_pieces_vs_oracle(golden):
+    """cv_to_array / recompute_matching / affinity_diagonal of cvx_proj_b200.spectral_method (host, numpy) against the
+    oracle and the live reference's masks; keypoints and matches are duck-typed stand-ins for cv2's objects."""
+    from types import SimpleNamespace
+    from cvx_proj_b200 import spectral_method as psm
+    from oracle import spectral_oracle as so
+    from oracle.gen_golden_spectral import OPTS, spectral_case
+    g = golden("ref_spectral.npz")
+    opts = SimpleNamespace(**OPTS)
+    for name in ("s40", "s300", "s1000"):
+        c, o, cf, of, fmat, hg = spectral_case(name)
+        n = c.shape[0]
+        perm = np.random.default_rng(1).permutation(n)
+        kc = [SimpleNamespace(pt=(float(x), float(y))) for x, y in c[np.argsort(perm)]]     # stored shuffled ...
+        fc = cf[np.argsort(perm)]
+        ko = [SimpleNamespace(pt=(float(x), float(y))) for x, y in o]
+        matches = [SimpleNamespace(queryIdx=int(perm[i]), trainIdx=i) for i in range(n)]       # ... matches undo it
+        sp, dp = psm.cv_to_array(kc, ko, matches)
+        assert np.array_equal(sp, c) and np.array_equal(dp, o)
+        mask = psm.recompute_matching(kc, fc, ko, of, matches, hg, opts)
+        assert np.array_equal(mask, g[name + "_original_mask"])
+        diag = psm.affinity_diagonal(c, o, cf, of, fmat, OPTS["epi_weight"])
+        want = np.diag(so.affinity_matrix(c, o, cf, of, fmat, OPTS["epi_weight"], OPTS["affinity_eps"]))
+        assert np.array_equal(diag, want)

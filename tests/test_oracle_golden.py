@@ -145,3 +145,16 @@ def test_image_warping_oracle_reproduces_live_reference(golden):
             assert hashlib.sha256(res.tobytes()).hexdigest() == str(g[tag + "_sha"]), tag
             if name in FULL:
                 assert np.array_equal(res, g[tag])
+
+
+def test_spectral_oracle_reproduces_live_reference(golden):
+    """oracle/spectral_oracle.py against outputs of the live reference's calculate_M (oracle/gen_golden_spectral.py)."""
+    from oracle import spectral_oracle as so
+    from oracle.gen_golden_spectral import CASES, OPTS, spectral_case
+    g = golden("ref_spectral.npz")
+    for name in ("s40", "s300", "s1000"):
+        c, o, cf, of, fmat, hg = spectral_case(name)
+        seg, rmask, omask = so.calculate_m(c, o, cf, of, fmat, hg, **OPTS)
+        assert np.array_equal(seg, g[name + "_segment"])
+        assert np.array_equal(rmask, g[name + "_ransac_mask"]) and np.array_equal(omask, g[name + "_original_mask"])
+    assert set(CASES) == {"s40", "s300", "s1000", "s2500"}
