@@ -16,7 +16,11 @@ dev = torch.device("cuda", 0)
 p = bench.Pass(torch, dev, name)
 p.gram(); p.eig()
 p.prepare_warp()
-from cvx_proj_b200 import utils as putils  # noqa: E402
+from cvx_proj_b200 import spectral_method as psm, synth, utils as putils  # noqa: E402
+import numpy as np  # noqa: E402
+
+sp_o, sp_c, _h = synth.make_keypoints(1024, 768, 2500, seed=11)
+sp_diag = np.full(2500, 0.95)
 
 g_cw, g_ch, g_tx, g_ty, g_m = putils.warping_canvas(p.host_img.shape, p.host_img.shape, p.sc.h_gt)
 g_out = torch.empty((g_ch, g_cw, 3), dtype=torch.uint8, device=dev)
@@ -33,5 +37,7 @@ for _ in range(iters):
     p.prepare_warp()                                    # k_warp_prep (+ uploads)
     p.warp(False); p.warp(True); p.blend()
     gw(0); gw(1); gw(2)                                 # k_warp_global: warp only, paste, mean blend
+    if _ == 0:
+        psm.spectral_segment_device(sp_c, sp_o, sp_diag, 30.0, device=dev)   # k_affinity, k_matvec, k_rescale
 torch.cuda.synchronize()
 print("profile pass ok", name, iters)
