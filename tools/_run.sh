@@ -1,7 +1,8 @@
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01n.json 2> gpurun_out/bench_r01n.err; echo "rc=$?"; tail -3 gpurun_out/bench_r01n.err
-python - <<'PY'
+N=${1:-4}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?"; tail -3 gpurun_out/bench_${N}gpu.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_r01n.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['spectral'], d['global_warp']['ms_per_step'], d['gpu_launches'])
+d=json.loads(open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","n_gpus","ms_per_step","scaling")}); print(json.dumps(d.get("c3_sharded")))
 PY
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 bench.py --impl reference --gpus $N --steps 2 --warmup 1 | tail -1 | cut -c1-200
