@@ -580,6 +580,32 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
             mark(); sharding.gather_bands(p.canvas, shards, sc0.final_w); mark()
         (t_gather,) = timed_steps(torch, flush, W, K, gather_body, 2)
         barrier()
+    # the panorama assembled by the warp kernel itself: row band stored into every GPU through the NVLS multicast mapping
+    ms_fused = None
+    if world > 1:
+        sym = sharding.SymmetricPanorama(sc0.final_h, sc0.final_w, device)
+        if sym.supported:
+            own = sym.local[me.px_row0:me.px_row1]
+
+            def fused_body(mark):
+                mark()
+                p.st.warp_device(p.img, p.tables, p.sc.mesh_cells, out=own)     # the band, straight into the panorama
+                sym.broadcast_band(me.px_row0, me.px_row1)                      # ... and into everyone else's
+                sym.barrier()
+                mark()
+            (t_fused,) = timed_steps(torch, flush, W, K, fused_body, 2)
+            barrier()
+            ms_fused = max_over_ranks(t_fused)
+            # every band of this rank's panorama must be the band its owner warped (checksums travel over NCCL)
+            def checksum(t):
+                v = t.reshape(-1).to(torch.int64)
+                return (v * (torch.arange(v.numel(), device=device, dtype=torch.int64) % 8191 + 1)).sum()
+            sums = [torch.zeros((), dtype=torch.int64, device=device) for _ in range(world)]
+            dist.all_gather(sums, checksum(p.canvas))
+            same = all(bool(checksum(sym.local[s.px_row0:s.px_row1]) == sums[s.rank]) for s in shards)
+            everyone = torch.tensor([int(same)], device=device)
+            dist.all_reduce(everyone, op=dist.ReduceOp.MIN)
+            assert bool(everyone.item()), "assembled panorama differs from the bands"
     ms_dlt = max_over_ranks(t_dlt)
     ms_warp = max_over_ranks(t_warp)
     ms_gather = max_over_ranks(t_gather)
@@ -587,6 +613,11 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
             "cells_per_s": sc0.n_cells / (ms_dlt * 1e-3), "dlt_ms": ms_dlt, "gram_ms": max_over_ranks(t_gram),
             "warp_mpix_per_s": sc0.canvas_px / (ms_warp * 1e-3) / 1e6, "warp_ms": ms_warp,
             "allgather_ms": ms_gather, "allgather_bytes": 3 * sc0.canvas_px,
+            "warp_and_assemble_ms": ms_fused,
+            "warp_and_assemble_note": "warp into the rank's panorama (symmetric memory) + broadcast of the band into every "
+                                      "other GPU's panorama (NVLS multimem.st kernel; a peer copy at 2 GPUs) + group barrier: "
+                                      "replaces warp_ms + allgather_ms; null without NVSwitch multicast. Every GPU receives "
+                                      "(N-1)/N of the panorama over NVLink either way",
             "shard": "cell rows + canvas row bands per rank; keypoints and source image replicated",
             "_launches": 5 * K}
 

@@ -695,13 +695,17 @@ class APAP:
         return WarpTables(fast, hinv_dev, views[1].view(torch.int32), views[2].view(torch.int32),
                           int(blocks.shape[0]), int(row0), int(row1))
 
-    def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False):
+    def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False, multicast_ptr=None):
         """Device-resident K3 (optionally fused with K4): writes the canvas rows ``[tables.row0,
-        tables.row1)`` into ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None)."""
+        tables.row1)`` into ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None).
+        ``multicast_ptr``: address of canvas row ``tables.row0`` inside an NVLS multicast mapping of a panorama buffer
+        that every GPU of the group holds (``sharding.SymmetricPanorama``): the band is stored into all of them by
+        the kernel itself and ``out`` is not written."""
         torch, device = rt.torch_cuda(src_dev.device)
         lib = rt.load_library()
         fw = int(self.final_width)
-        if out is None:
+        n_bytes = (tables.row1 - tables.row0) * fw * 3
+        if multicast_ptr is None and out is None:
             out = torch.empty((tables.row1 - tables.row0, fw, 3), dtype=torch.uint8, device=device)
         ch, cw = (centre_dev.shape[0], centre_dev.shape[1]) if centre_dev is not None else (0, 0)
         with torch.cuda.device(device):
@@ -709,8 +713,10 @@ class APAP:
                 src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
                 tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_blocks.data_ptr(),
                 tables.n_blocks, grid_cols, fw, int(self.offset_x), int(self.offset_y), tables.row0,
-                centre_dev.data_ptr() if centre_dev is not None else None, ch, cw, out.data_ptr(),
-                out.numel(), int(force_exact), rt.stream_ptr(torch, device)), "apap_warp")
+                centre_dev.data_ptr() if centre_dev is not None else None, ch, cw,
+                int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
+                n_bytes if multicast_ptr is not None else out.numel(), int(force_exact),
+                1 if multicast_ptr is not None else 0, rt.stream_ptr(torch, device)), "apap_warp")
         return out
 
     def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False):

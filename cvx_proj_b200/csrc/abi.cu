@@ -111,19 +111,26 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
               const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w,
               int off_x, int off_y, int row0, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
-              size_t out_band_bytes, int force_exact, void *stream) {
+              size_t out_band_bytes, int force_exact, int multicast, void *stream) {
   if (!src || !cell_fast || !cell_hinv || !col_lut || !out_band) return fail(APAP_E_BADARG, "null pointer");
   if (n_blocks < 0 || (n_blocks > 0 && !row_blocks)) return fail(APAP_E_BADARG, "warp: bad row blocks");
   if (src_h <= 0 || src_w <= 0 || canvas_w <= 0 || grid_cols <= 0) return fail(APAP_E_BADARG, "warp: sizes must be > 0");
   if (centre && (centre_h <= 0 || centre_w <= 0)) return fail(APAP_E_BADARG, "warp: bad centre image size");
   return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, row_blocks, n_blocks, grid_cols, canvas_w, off_x,
                      off_y, row0, centre, centre_h, centre_w, out_band, out_band_bytes, force_exact,
-                     static_cast<cudaStream_t>(stream));
+                     multicast, static_cast<cudaStream_t>(stream));
 }
 
 int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream) {
   if (!a || !b || !out) return fail(APAP_E_BADARG, "null pointer");
   return launch_blend(a, b, out, n_px, static_cast<cudaStream_t>(stream));
+}
+
+int apap_multicast_copy(const void *src, void *multicast_dst, size_t bytes, void *stream) {
+  if (!src || !multicast_dst) return fail(APAP_E_BADARG, "multicast_copy: null pointer");
+  if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(multicast_dst) & 15u))
+    return fail(APAP_E_ALIGN, "multicast_copy: size and both addresses must be multiples of 16 bytes");
+  return launch_multicast_copy(src, multicast_dst, bytes, static_cast<cudaStream_t>(stream));
 }
 
 int apap_pipe_probe(int kind, int iters, float *sink, double *ops, void *stream) {

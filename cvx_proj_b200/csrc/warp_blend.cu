@@ -57,7 +57,15 @@ struct WarpParams {
   int off_x, off_y;
   int centre_h, centre_w;
   int force_exact;
+  int multicast;               // out is an NVLS multicast address: every store goes to all GPUs of the group
 };
+
+// One 32-bit store to every replica of a multicast (NVLS) mapping: the NVSwitch fans it out.
+__device__ __forceinline__ void multimem_st_v4(void *mc_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
 
 constexpr float kMagic = 12582912.f;          // 1.5 * 2^23: x + kMagic (round down) = floor(x) in the mantissa
 
@@ -188,7 +196,9 @@ __device__ __forceinline__ void block_store(const WarpParams &p, int i0, int n_r
                                             const uint32_t (&b1)[kBlockRows], const uint32_t (&b2)[kBlockRows],
                                             const uint32_t (&c0)[kBlockRows], const uint32_t (&c1)[kBlockRows],
                                             const uint32_t (&c2)[kBlockRows], uint32_t lane_off, uint32_t pitch,
-                                            int lane_a, int lane_b, uint32_t sel, bool store_ok) {
+                                            int lane_a, int lane_b, uint32_t sel, int n_store) {
+  // n_store: 32-bit words this warp writes per row (kWords), or 1 / 0 for a valid / invalid column (byte stores)
+  const bool store_ok = (int)(threadIdx.x & 31) < n_store || (!kWords && n_store > 0);
   uint8_t *d = p.out + ((uint32_t)(i0 - p.row0) * pitch + lane_off);   // the band is < 2^31 bytes (launch_warp)
 #pragma unroll
   for (int k = 0; k < kBlockRows; ++k) {
@@ -201,7 +211,18 @@ __device__ __forceinline__ void block_store(const WarpParams &p, int i0, int n_r
       if (kWords) {
         const uint32_t va = __shfl_sync(0xffffffffu, val, lane_a);
         const uint32_t vb = __shfl_sync(0xffffffffu, val, lane_b);
-        if (store_ok) *reinterpret_cast<uint32_t *>(d) = __byte_perm(va, vb, sel);
+        const uint32_t word = __byte_perm(va, vb, sel);
+        if (p.multicast) {                         // warp-uniform
+          // NVLS stores, 16 bytes each (4-byte packets waste the links): lane l < 6 collects the words 4l .. 4l+3 of
+          // the row's 24 and stores them with one multimem.st.v4 (launch_warp checks canvas_w % 16 == 0, so a row
+          // segment is a whole number of 16-byte groups, 16-byte aligned)
+          const int lane = threadIdx.x & 31, l4 = (lane << 2) & 31;
+          const uint32_t w0 = __shfl_sync(0xffffffffu, word, l4), w1 = __shfl_sync(0xffffffffu, word, l4 + 1);
+          const uint32_t w2 = __shfl_sync(0xffffffffu, word, l4 + 2), w3 = __shfl_sync(0xffffffffu, word, l4 + 3);
+          if (4 * lane + 3 < n_store) multimem_st_v4(d + 12 * lane, w0, w1, w2, w3);   // d + 12 lane = row segment + 16 lane
+        } else if (store_ok) {
+          *reinterpret_cast<uint32_t *>(d) = word;
+        }
       } else if (store_ok) {
         d[0] = (uint8_t)val;
         d[1] = (uint8_t)(val >> 8);
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(kWarpThreads, APAP_WARP_CTAS) k_warp(const War
   // and lane_a + 1, starting at byte (4w) % 3 of the first
   const int lane_a = (lane + lane / 3) & 31, lane_b = (lane_a + 1) & 31;
   const uint32_t sel = (lane % 3 == 0) ? 0x4210u : (lane % 3 == 1) ? 0x5421u : 0x6542u;
-  const bool store_ok = kWords ? lane < min(24, (3 * (p.canvas_w - j0)) >> 2) : col_ok;
+  const int store_ok = kWords ? min(24, (3 * (p.canvas_w - j0)) >> 2) : (col_ok ? 1 : 0);   // words per row / column valid
   const uint32_t pitch = (uint32_t)p.canvas_w * 3u;
   const uint32_t lane_off = (uint32_t)j0 * 3u + (kWords ? 4u : 3u) * lane;
 
@@ -354,7 +375,7 @@ __global__ void __launch_bounds__(kBlendThreads) k_blend(const uint4 *__restrict
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
                 const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w,
                 int off_x, int off_y, int row0, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
-                size_t out_band_bytes, int force_exact, cudaStream_t st) {
+                size_t out_band_bytes, int force_exact, int multicast, cudaStream_t st) {
   if ((long long)src_w * src_h > 2147483647LL)
     return fail(APAP_E_TOOBIG, "warp: source image has more than 2^31-1 pixels");
   if ((reinterpret_cast<uintptr_t>(cell_fast) & 15u) || (reinterpret_cast<uintptr_t>(col_lut) & 7u) ||
@@ -371,11 +392,14 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
   p.chunks_per_row = (canvas_w + 31) / 32;
   p.src_h = src_h; p.src_w = src_w; p.grid_cols = grid_cols; p.canvas_w = canvas_w;
   p.off_x = off_x; p.off_y = off_y; p.centre_h = centre_h; p.centre_w = centre_w; p.force_exact = force_exact;
+  p.multicast = multicast;
 #ifdef APAP_WARP_NOWORDS
   const bool words = false;                        // lab: byte stores always
 #else
   const bool words = (canvas_w % 4 == 0) && !(reinterpret_cast<uintptr_t>(out_band) & 3u);
 #endif
+  if (multicast && (!words || canvas_w % 16 != 0 || (reinterpret_cast<uintptr_t>(out_band) & 15u)))
+    return fail(APAP_E_ALIGN, "warp: multicast stores need canvas_w % 16 == 0 and a 16-byte aligned band");
   // one resident wave: grid.x CTAs side by side cover the canvas width, grid.y of them share its height
   const int gx = (p.chunks_per_row + kWarpsPerCta - 1) / kWarpsPerCta;
   const int visits = (n_blocks + 1) / 2;           // a visit = two consecutive row blocks

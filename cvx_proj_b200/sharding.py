@@ -81,6 +81,58 @@ def gather_bands(band, shards, canvas_w: int, group=None):
     return torch.cat(parts, dim=0).reshape(-1, canvas_w, 3)
 
 
+class SymmetricPanorama:
+    """The panorama buffer of a sharded pass as torch symmetric memory: one ``[canvas_h, canvas_w, 3]`` uint8 buffer
+    per GPU, mapped into every peer, plus the NVLS multicast mapping of all of them.  The warp kernel stores its row
+    band through the multicast address (``multimem.st``): the NVSwitch delivers it to every GPU, so when the group has
+    passed ``barrier()`` each rank holds the complete panorama -- the assembly is fused into the warp and there is
+    no all-gather.  Needs NVSwitch multicast (``multicast_ptr`` non-zero) and ``canvas_w % 16 == 0`` (16-byte stores)."""
+
+    def __init__(self, canvas_h: int, canvas_w: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.canvas_h, self.canvas_w = int(canvas_h), int(canvas_w)
+        self.local = symm_mem.empty((self.canvas_h, self.canvas_w, 3), dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.local, self.group)
+        self.multicast_ptr = int(self.handle.multicast_ptr or 0)
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self._peers = None
+
+    @property
+    def supported(self) -> bool:
+        return self.multicast_ptr != 0 and self.canvas_w % 16 == 0
+
+    def band_ptr(self, px_row0: int) -> int:
+        return self.multicast_ptr + int(px_row0) * self.canvas_w * 3
+
+    def broadcast_band(self, px_row0: int, px_row1: int):
+        """Store the canvas rows ``[px_row0, px_row1)`` of this rank's panorama into every GPU's (``apap_multicast_copy``)."""
+        import torch
+
+        from . import _runtime as rt
+
+        band = self.local[px_row0:px_row1]
+        if band.numel() == 0:
+            return
+        if self.world == 2:
+            # two GPUs: one unicast peer copy beats the multicast store rate (measured 129 us against 190 us for
+            # the 62 MB band of c3); from three GPUs on a rank would send its band N - 1 times and multicast wins
+            if self._peers is None:
+                self._peers = [self.handle.get_buffer(r, tuple(self.local.shape), torch.uint8) for r in range(self.world)]
+            self._peers[1 - self.rank][px_row0:px_row1].copy_(band, non_blocking=True)
+            return
+        with torch.cuda.device(self.local.device):
+            rt.check(rt.load_library().apap_multicast_copy(band.data_ptr(), self.band_ptr(px_row0), band.numel(),
+                                                           rt.stream_ptr(torch, self.local.device)), "apap_multicast_copy")
+
+    def barrier(self):
+        """Every rank's band has landed everywhere once all ranks are past this (device-side, on the current stream)."""
+        self.handle.barrier()
+
+
 class ShardedAPAP:
     """One APAP pass split over the ranks of a ``torch.distributed`` group.
 
@@ -125,3 +177,29 @@ class ShardedAPAP:
 
     def panorama(self, band, group=None):
         return gather_bands(band, self.shards, int(self.stitcher.final_width), group)
+
+    def local_warp_panorama(self, ori_img, local_h_rows, pano: "SymmetricPanorama", fused_stores: bool = False):
+        """``local_warp_band`` + ``panorama`` without an all-gather: the owned canvas rows are warped into this rank's
+        panorama and broadcast into every other GPU's through the NVLS multicast mapping (``fused_stores``: by the
+        warp kernel's own stores instead of a broadcast kernel -- one kernel, but its 96-byte row fragments use the
+        links 2.5x worse); returns this rank's (complete) panorama tensor."""
+        from . import _runtime as rt
+        from .apap import invert_grid_inplace
+
+        st, s = self.stitcher, self.me
+        torch, device = rt.torch_cuda(st.device)
+        invert_grid_inplace(local_h_rows)
+        full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
+        full[...] = np.eye(3, dtype=np.float32)
+        full[s.cell_row0:s.cell_row1] = local_h_rows
+        src_dev = ori_img if not isinstance(ori_img, np.ndarray) else rt.to_device(torch, device, ori_img)
+        tables = st.warp_tables_device(full, self.col_cell, self.row_cell, int(ori_img.shape[1]),
+                                       int(ori_img.shape[0]), device, s.px_row0, s.px_row1)
+        if fused_stores:
+            st.warp_device(src_dev, tables, self.grid_cols, multicast_ptr=pano.band_ptr(s.px_row0))
+        else:
+            band = pano.local[s.px_row0:s.px_row1]
+            st.warp_device(src_dev, tables, self.grid_cols, out=band)
+            pano.broadcast_band(s.px_row0, s.px_row1)
+        pano.barrier()
+        return pano.local

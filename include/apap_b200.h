@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 8
+#define APAP_ABI_VERSION 10
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -146,12 +146,17 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
  *               the warped pixel by the uniform_blend rule (fused K3+K4, pyviz/apap.py:259-261);
  *               NULL = plain warp
  *   force_exact : non-zero = every pixel takes the float64 path (validation switch)
+ *   multicast   : non-zero = out_band is an NVLS multicast address (one mapping of the same panorama buffer on every
+ *                 GPU of the group, e.g. torch symmetric memory's multicast_ptr + band offset): the kernel stores with
+ *                 multimem.st, so the NVSwitch writes this rank's row band into every GPU's panorama -- the panorama
+ *                 is assembled by the warp itself, no all-gather.  Stores are 16 bytes wide: needs canvas_w % 16 == 0 and a
+ *                 16-byte aligned band; the caller synchronises the group afterwards.
  */
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
               const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols,
               int canvas_w, int off_x, int off_y, int row0,
               const uint8_t *centre, int centre_h, int centre_w,
-              uint8_t *out_band, size_t out_band_bytes, int force_exact, void *stream);
+              uint8_t *out_band, size_t out_band_bytes, int force_exact, int multicast, void *stream);
 
 /*
  * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,
@@ -207,6 +212,15 @@ int apap_affinity_matrix(const float *src_pts, const float *dst_pts, const doubl
                          double *m, void *stream);
 int apap_power_step(const double *m, int n, double *x, double *y, double *norm_sq,
                     unsigned long long *max_diff_bits, void *stream);
+
+/*
+ * Panorama assembly of a sharded pass without an all-gather: broadcast `bytes` of device memory at `src` (this
+ * rank's row band, already warped) into every GPU's panorama through an NVLS multicast mapping -- `multicast_dst` is
+ * the band's address inside the multicast mapping of the panorama buffers (torch symmetric memory's multicast_ptr +
+ * offset).  One 16-byte multimem store per 16 bytes: the NVSwitch replicates it, so a rank sends its band once
+ * whatever the number of GPUs.  Size and both addresses must be multiples of 16; the caller synchronises the group.
+ */
+int apap_multicast_copy(const void *src, void *multicast_dst, size_t bytes, void *stream);
 
 /*
  * Pipe probes for the roofline denominators that MEASURED_PEAKS.json does not hold.  Runs `iters` x 16

@@ -1,8 +1,7 @@
 N=${1:-4}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?"; tail -3 gpurun_out/bench_${N}gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?"; tail -3 gpurun_out/bench_${N}gpu.err
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ("value","n_gpus","ms_per_step","scaling")}); print(json.dumps(d.get("c3_sharded")))
+c=d["c3_sharded"]; print(d['value'], {k:c[k] for k in ("dlt_ms","warp_ms","allgather_ms","warp_and_assemble_ms")})
 PY
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 bench.py --impl reference --gpus $N --steps 2 --warmup 1 | tail -1 | cut -c1-200

@@ -28,6 +28,19 @@ for name, kw in (("mini", {}), ("c1", {}), ("c2", {})):
     h_rows = sh.local_homography(sc.src, sc.dst, sc.vertices)
     band = sh.local_warp_band(img, h_rows.copy())
     pano = sh.panorama(band).cpu().numpy()
+    # the same panorama assembled by the warp kernel itself: multimem.st through the NVLS multicast mapping
+    sym = sharding.SymmetricPanorama(sc.final_h, sc.final_w, dev)
+    fused = None
+    if sym.supported:
+        sym.local.fill_(7)
+        dist.barrier()
+        fused = sh.local_warp_panorama(img, h_rows.copy(), sym)
+        torch.cuda.synchronize()
+        fused = fused.cpu().numpy()
+    same_f = True if fused is None else bool(np.array_equal(fused, pano))
+    flags = torch.tensor([int(same_f)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    same_f_all = bool(flags.item())
     # gather the H rows too (host side, via the same process group on device tensors)
     h_dev = torch.from_numpy(np.ascontiguousarray(h_rows)).to(dev)
     sizes = [s.n_cell_rows for s in sh.shards]
@@ -41,9 +54,10 @@ for name, kw in (("mini", {}), ("c1", {}), ("c2", {})):
         one = st.local_warp(img, h_one.copy(), sc.mesh)
         same_h = np.array_equal(h_all.view(np.uint32), h_one.view(np.uint32))
         same_p = np.array_equal(pano, one)
-        ok = ok and same_h and same_p
+        ok = ok and same_h and same_p and same_f_all
         print(f"{name}: {world} ranks over NCCL, H grid bit-identical to 1 GPU: {same_h}; panorama "
-              f"({pano.shape[1]}x{pano.shape[0]}) bit-identical: {same_p}; bands "
+              f"({pano.shape[1]}x{pano.shape[0]}) bit-identical: {same_p}; panorama assembled by multicast stores "
+              f"{'(no NVLS / canvas_w % 4 != 0: skipped)' if fused is None else 'identical on every rank: ' + str(same_f_all)}; bands "
               f"{[(s.px_row0, s.px_row1) for s in sh.shards]}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
