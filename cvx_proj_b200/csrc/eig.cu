@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(kEigThreads, 3) k_eig(const float *partials, c
   double h[9] = {0.31, -0.17, 0.43, 0.29, 0.37, -0.23, 0.41, 0.19, 0.47};
   int iters = 0;
   bool settled = false;
+  double prev_diff = 1.0;                              // the change of the previous step ~ the error before it
   for (; iters < kMaxInvIter && !settled; ++iters) {
     double y[9];
 #pragma unroll
@@ -283,7 +284,12 @@ __global__ void __launch_bounds__(kEigThreads, 3) k_eig(const float *partials, c
       diff = fmax(diff, fabs(yi - h[i]));
       h[i] = yi;
     }
-    settled = diff <= 1e-10;
+    // Inverse iteration contracts the error by rho = lambda_0 / lambda_1 per step and `diff` is the error of the
+    // PREVIOUS iterate, so the new one is within ~ diff * rho: stop when that is below 1e-11 (the output is float32),
+    // with rho estimated from the last two changes (never trusted below 1e-3 per step, and not before step 2)
+    const double rho = fmin(fmax(diff / prev_diff, 1e-3), 1.0);
+    settled = diff <= 1e-10 || (iters >= 1 && diff * rho <= 1e-11);
+    prev_diff = fmax(diff, 1e-300);
   }
   if (!settled || force_jacobi) {
     eig_cell_jacobi(partials, tmats, cells_padded, k_splits, cell, dst, sw);
