@@ -432,7 +432,7 @@ int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int 
   const int kb_per_split = p.chunks_per_split * (kChunk / kKB);
   dim3 grid(p.k_splits, (cells + 127) / 128, batch);
   if (grid.y > 65535 || batch > 65535) return fail(APAP_E_TOOBIG, "gram: more than 65535 cell tiles (8.3 M cells) or scenes per launch");
-  if (APAP_TC_POLY > 0 && gamma_sq >= 0.25f)
+  if (APAP_TC_POLY > 0 && gamma_sq >= 0.25f && gamma_sq <= 1.f)   // the polynomial covers 2^-t for t in [0, 2]
     k_gram_tc<APAP_TC_POLY><<<grid, kTcThreads, sizeof(TcSmem), st>>>(kp_blocks, anchors, cells, p.cells_padded, n_kb,
                                                                       kb_per_split, p.k_splits, gamma_sq, partials, tile_done);
   else

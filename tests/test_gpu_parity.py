@@ -99,7 +99,8 @@ def test_ragged_keypoint_counts(n_kp, engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("gamma,sigma", [(0.5, 100), (0.3, 100), (0.8, 100), (0.05, 20), (0.5, 8), (0.9999, 100)])
+@pytest.mark.parametrize("gamma,sigma", [(0.5, 100), (0.3, 100), (0.8, 100), (0.05, 20), (0.5, 8), (0.9999, 100),
+                                         (1.0, 100), (1.7, 50)])
 def test_clamp_and_falloff_sweep(gamma, sigma, engine):
     """gamma decides which weight path the tensor-core kernel takes (polynomial 2^-t for gamma >= 0.5,
     MUFU.EX2 below); sigma moves the weights between ~1 everywhere and clamped almost everywhere."""
