@@ -431,10 +431,10 @@ def run_ours(args):
         if k >= W:
             e2e_dlt.append(t1 - t0)
             e2e_warp.append(t2 - t1)
-    launches += 3 * K
+    launches += 6 * K          # k_kp_rows, k_kp_blocks, k_gram_tc, k_eig; k_warp_prep, k_warp
     e2e_dlt_s = max_over_ranks(float(np.mean(e2e_dlt)))
     e2e_warp_s = max_over_ranks(float(np.mean(e2e_warp)))
-    h2d_dlt = p.rows.numel() * 4 + p.cells * 8 + 144
+    h2d_dlt = 3 * sc.src.shape[0] * 8 + 4 + p.cells * 8 + 144     # conditioned pairs + raw points, count, anchors, matrices
     d2h_dlt = p.cells * 36
     h2d_warp = 3 * src_px + p.cells * 36 + 8 * sc.final_w + 8 * p.tables.n_blocks + 16 * sc.mesh_cells
     d2h_warp = 3 * canvas_px

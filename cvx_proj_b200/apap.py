@@ -527,38 +527,62 @@ class APAP:
         return target
 
     # ---- moving DLT ----------------------------------------------------------------------------
-    def _prepare(self, src_point, dst_point):
-        """Host prologue of ``local_homography`` (pyviz/apap.py:129-145): normalise, condition,
-        build the DLT matrix; then the keypoint ROW table (``build_kp_table``) and the two 3x3
-        de-normalisation matrices.  The tensor-core engine's block table is packed from the rows on the
-        device (``kp_table_device``)."""
+    def _condition(self, src_point, dst_point):
+        """The O(N) host prologue of ``local_homography`` (pyviz/apap.py:129-141): normalise and condition
+        both point sets with the reference's own numpy calls (their float32 reductions and the BLAS product
+        are kept on the host so every bit matches).  Returns the conditioned points ``cf1, cf2``
+        (``[N, 2]`` float32) and the two 3x3 de-normalisation matrices packed as ``[18]`` float64."""
         src_point = np.asarray(src_point)
         dst_point = np.asarray(dst_point)
-        sample_n, _ = src_point.shape
         n1, nf1 = self.getNormalize2DPts(src_point)
         n2, nf2 = self.getNormalize2DPts(dst_point)
         c1 = self.getConditionerFromPts(nf1)
         c2 = self.getConditionerFromPts(nf2)
         cf1 = self.point_normalize(nf1, c1)
         cf2 = self.point_normalize(nf2, c2)
-        dlt = self.matrix_generate(sample_n, cf1, cf2)
-        table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
         # h -> inv(N2) (inv(C2) h C1) N1   (pyviz/apap.py:165-166); inverses in float32 like the reference
         t2inv = np.linalg.inv(n2).astype(np.float64) @ np.linalg.inv(c2).astype(np.float64)
         t1 = c1.astype(np.float64) @ n1.astype(np.float64)
         tmats = np.concatenate([t2inv.reshape(9), t1.reshape(9)])
+        return cf1, cf2, tmats
+
+    def _prepare(self, src_point, dst_point):
+        """Host restatement of the device table build (tests, tools): ``_condition``, the DLT matrix
+        (pyviz/apap.py:143-145) and the keypoint ROW table (``build_kp_table``).  The product path builds the
+        same rows on the device (``kp_rows_device``) from the conditioned points."""
+        src_point = np.asarray(src_point)
+        cf1, cf2, tmats = self._condition(src_point, dst_point)
+        dlt = self.matrix_generate(src_point.shape[0], cf1, cf2)
+        table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
         return table, tmats
 
-    def _upload_scene(self, torch, device, tables, anchors, tmats):
-        """One host->device copy for all kernel inputs of ``batch`` scenes: the three arrays are
-        packed into a pinned staging buffer (kept per instance) and sliced on the device.
-        Layout: float32 tables [b, n_pad, 28] | float32 anchors [b, cells, 2] | float64 tmats [b, 18]
-        (every section starts 16-byte aligned)."""
+    def _upload_scene(self, torch, device, points, counts, anchors, tmats):
+        """One host->device copy for all kernel inputs of ``batch`` scenes: the arrays are packed into a pinned
+        staging buffer (kept per instance) and sliced on the device.
+        Layout: float32 points [3, b, n, 2] (conditioned source, conditioned target, raw source) |
+        int32 counts [b] | float32 anchors [b, cells, 2] | float64 tmats [b, 18] (every section starts 16-byte
+        aligned).  Returns the keypoint ROW table built from the points on the device, the anchors, the matrices."""
         if not hasattr(self, "_stage"):
             self._stage = _PinnedStage()
-        t_u8, a_u8, m_u8 = self._stage.upload(torch, device, (tables, anchors, tmats))
-        return (t_u8.view(torch.float32).view(tables.shape), a_u8.view(torch.float32).view(anchors.shape),
-                m_u8.view(torch.float64).view(tmats.shape))
+        p_u8, c_u8, a_u8, m_u8 = self._stage.upload(torch, device, (points, counts, anchors, tmats))
+        rows = self.kp_rows_device(p_u8.view(torch.float32).view(points.shape), c_u8.view(torch.int32))
+        return rows, a_u8.view(torch.float32).view(anchors.shape), m_u8.view(torch.float64).view(tmats.shape)
+
+    def kp_rows_device(self, points_dev, counts_dev=None):
+        """Keypoint ROW table ``[batch, n_pad, 28]`` built on the device by ``apap_kp_rows`` (same bits as
+        ``build_kp_table``) from ``points_dev`` = float32 ``[3, batch, n, 2]``: conditioned source points,
+        conditioned target points, raw source points; ``counts_dev`` int32 ``[batch]`` = matches per scene."""
+        torch, device = rt.torch_cuda(points_dev.device)
+        lib = rt.load_library()
+        _, batch, n, _ = points_dev.shape
+        n_pad = max(KP_CHUNK, (n + KP_CHUNK - 1) // KP_CHUNK * KP_CHUNK)
+        rows = torch.empty((batch, n_pad, KP_ROW), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_kp_rows(points_dev[0].data_ptr(), points_dev[1].data_ptr(), points_dev[2].data_ptr(),
+                                      counts_dev.data_ptr() if counts_dev is not None else None, batch, n, n_pad,
+                                      weight_scale(self.sigma), rows.data_ptr(), rt.stream_ptr(torch, device)),
+                     "apap_kp_rows")
+        return rows
 
     def kp_table_device(self, rows_dev):
         """Device keypoint table of this instance's Gram engine from the uploaded row table
@@ -625,11 +649,16 @@ class APAP:
         """
         sample_n, _ = np.shape(src_point)
         mesh_n, pt_size, _ = np.shape(vertices)
-        table, tmats = self._prepare(src_point, dst_point)
+        if sample_n == 0:
+            raise ValueError("local_homography needs at least one match")
+        cf1, cf2, tmats = self._condition(src_point, dst_point)
         torch, device = rt.torch_cuda(self.device)
         cells = mesh_n * pt_size
         anchors = scale_anchors(vertices, weight_scale(self.sigma))
-        t_dev, a_dev, m_dev = self._upload_scene(torch, device, table[None], anchors[None], tmats[None])
+        points = np.empty((3, 1, sample_n, 2), dtype=np.float32)
+        points[0, 0], points[1, 0], points[2, 0] = cf1, cf2, src_point
+        counts = np.array([sample_n], dtype=np.int32)
+        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors[None], tmats[None])
         h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, 1, cells)
         h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
         weight = LazyLocalWeight(np.asarray(src_point), np.asarray(vertices), self.gamma, self.sigma, self.device)
@@ -643,15 +672,18 @@ class APAP:
         verts = vertices if isinstance(vertices, (list, tuple)) else [vertices] * count
         mesh_n, pt_size, _ = np.shape(verts[0])
         cells = mesh_n * pt_size
-        prepared = [self._prepare(s, d) for s, d in zip(src_points, dst_points)]
-        n_pad = max(t.shape[0] for t, _ in prepared)
-        tables = np.zeros((count, n_pad, prepared[0][0].shape[1]), dtype=np.float32)
-        for k, (t, _) in enumerate(prepared):
-            tables[k, :t.shape[0]] = t
-        tmats = np.stack([m for _, m in prepared])
+        prepared = [self._condition(s, d) for s, d in zip(src_points, dst_points)]
+        counts = np.array([cf1.shape[0] for cf1, _, _ in prepared], dtype=np.int32)
+        if count == 0 or counts.min() == 0:
+            raise ValueError("local_homography_batch needs at least one pair and one match per pair")
+        points = np.zeros((3, count, int(counts.max()), 2), dtype=np.float32)
+        for k, (cf1, cf2, _) in enumerate(prepared):
+            points[0, k, :counts[k]], points[1, k, :counts[k]] = cf1, cf2
+            points[2, k, :counts[k]] = src_points[k]
+        tmats = np.stack([m for _, _, m in prepared])
         anchors = np.stack([scale_anchors(v, weight_scale(self.sigma)) for v in verts])
         torch, device = rt.torch_cuda(self.device)
-        t_dev, a_dev, m_dev = self._upload_scene(torch, device, tables, anchors, tmats)
+        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors, tmats)
         h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, count, cells)
         h = rt.to_host(torch, h_dev).reshape(count, mesh_n, pt_size, 3, 3)
         return [h[k] for k in range(count)]

@@ -2,15 +2,61 @@
 // public calls (measured at c2: ~6 ms of table building against a 33 us warp kernel; the per-cell inverse of
 // pyviz/apap.py:201-203 stays numpy's own LAPACK call on the host -- its float32 results are the float64 dgesv
 // of OpenBLAS rounded once, and no other arithmetic reproduces every bit of them):
+//   k_kp_rows     conditioned keypoint pairs -> keypoint row table  (host restatement: apap.build_kp_table)
 //   k_kp_blocks   keypoint row table -> tensor-core block table (host restatement: apap.build_kp_blocks)
 //   k_warp_prep   per-cell fast-path records of the mesh warp   (host restatement: apap.build_warp_tables)
-// The two kernels reproduce their numpy restatements bit for bit (explicit _rn arithmetic, no FMA
+// The kernels reproduce their numpy restatements bit for bit (explicit _rn arithmetic, no FMA
 // contraction, same operation order), so the CPU tests of the guard band cover the device-built tables.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace apap {
+
+// ------------------------------------------------------------------------------------ k_kp_rows
+// One thread per keypoint row.  apap.build_kp_table: with (x, y) the conditioned source point, (x', y') the
+// conditioned target, m = [xx, xy, x, yy, y, 1] in float64 (exact products of float32 inputs), the row is
+// float32 of [m | x' m | y' m | (x'x' + y'y') m], then the raw source point times `scale`, each coordinate twice.
+// Rows at and past the scene's keypoint count are zero.
+__global__ void __launch_bounds__(128) k_kp_rows(const float2 *__restrict__ cf1, const float2 *__restrict__ cf2,
+                                                  const float2 *__restrict__ src, const int *__restrict__ counts,
+                                                  int n_points, int n_pad, double scale, float *__restrict__ rows) {
+  const int scene = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  const int n = counts ? min(counts[scene], n_points) : n_points;
+  float4 *dst = reinterpret_cast<float4 *>(rows + ((size_t)scene * n_pad + i) * kRowFloats);
+  float v[kRowFloats];
+  if (i < n) {
+    const size_t at = (size_t)scene * n_points + i;
+    const float2 a = cf1[at], b = cf2[at], k = src[at];
+    const double x = a.x, y = a.y, xp = b.x, yp = b.y;
+    const double m[6] = {__dmul_rn(x, x), __dmul_rn(x, y), x, __dmul_rn(y, y), y, 1.0};
+    const double r = __dadd_rn(__dmul_rn(xp, xp), __dmul_rn(yp, yp));
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      v[t] = __double2float_rn(m[t]);
+      v[6 + t] = __double2float_rn(__dmul_rn(xp, m[t]));
+      v[12 + t] = __double2float_rn(__dmul_rn(yp, m[t]));
+      v[18 + t] = __double2float_rn(__dmul_rn(r, m[t]));
+    }
+    v[24] = v[25] = __double2float_rn(__dmul_rn((double)k.x, scale));
+    v[26] = v[27] = __double2float_rn(__dmul_rn((double)k.y, scale));
+  } else {
+#pragma unroll
+    for (int t = 0; t < kRowFloats; ++t) v[t] = 0.f;
+  }
+#pragma unroll
+  for (int t = 0; t < kRowFloats / 4; ++t) dst[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+}
+
+int launch_kp_rows(const float *cf1, const float *cf2, const float *src, const int *counts, int batch, int n_points,
+                   int n_kp_padded, double scale, float *rows, cudaStream_t st) {
+  if (batch == 0 || n_kp_padded == 0) return 0;
+  dim3 grid((n_kp_padded + 127) / 128, batch);
+  k_kp_rows<<<grid, 128, 0, st>>>(reinterpret_cast<const float2 *>(cf1), reinterpret_cast<const float2 *>(cf2),
+                                  reinterpret_cast<const float2 *>(src), counts, n_points, n_kp_padded, scale, rows);
+  return check_cuda(cudaGetLastError(), "k_kp_rows launch");
+}
 
 // ------------------------------------------------------------------------------------ k_kp_blocks
 // Block layout (include/apap_b200.h): per 8 keypoints the 8 x 64 tile [Ph | Pl] in the K-major
@@ -179,6 +225,19 @@ int launch_warp_prep(const float *inv_h, const int *col_ext, const int *row_ext,
 using namespace apap;
 
 extern "C" {
+
+int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_raw, const int *counts, int batch,
+                 int n_points, int n_kp_padded, double scale, float *kp_table, void *stream) {
+  if (!src_cond || !dst_cond || !src_raw || !kp_table) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || n_points <= 0 || n_kp_padded < n_points || n_kp_padded % kChunk)
+    return fail(APAP_E_BADARG, "kp_rows: bad sizes");
+  if ((reinterpret_cast<uintptr_t>(src_cond) | reinterpret_cast<uintptr_t>(dst_cond) |
+       reinterpret_cast<uintptr_t>(src_raw)) & 7u)
+    return fail(APAP_E_ALIGN, "kp_rows: the point arrays must be 8-byte aligned");
+  if (reinterpret_cast<uintptr_t>(kp_table) & 15u) return fail(APAP_E_ALIGN, "kp_rows: kp_table must be 16-byte aligned");
+  return launch_kp_rows(src_cond, dst_cond, src_raw, counts, batch, n_points, n_kp_padded, scale, kp_table,
+                        static_cast<cudaStream_t>(stream));
+}
 
 int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream) {
   if (!kp_table || !kp_blocks) return fail(APAP_E_BADARG, "null pointer");

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 10
+#define APAP_ABI_VERSION 11
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -168,6 +168,13 @@ int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, vo
  * Input preparation on the device (what the host layer used to build in numpy; both reproduce their
  * numpy restatements in cvx_proj_b200/apap.py bit for bit).
  *
+ * apap_kp_rows: the keypoint row table (layout under apap_gram_partials) from the conditioned keypoint pairs --
+ * the Gram terms of the two DLT rows pyviz/apap.py:106-118 builds per match, float64 products rounded once.
+ *   src_cond, dst_cond : float [batch][n_points][2], the conditioned source / target points (pyviz/apap.py:136-141)
+ *   src_raw            : float [batch][n_points][2], the raw source points the weights are measured from (:150)
+ *   counts             : int32 [batch] matches per scene (rows past it are zero), or NULL = n_points everywhere
+ *   scale              : 2 log2(e) / sigma^2;  kp_table : float [batch][n_kp_padded][APAP_KP_ROW] (out)
+ *
  * apap_kp_blocks: the keypoint row table of engine FFMA2 -> the block table of engine TCGEN05 (layouts under
  * apap_gram_partials; the TF32 split of the product terms pyviz/apap.py:106-118 feeds the tensor cores).
  *   kp_table : float [batch][n_kp_padded][APAP_KP_ROW];  kp_blocks : float [batch][n_kp_padded / 8][APAP_KP_BLOCK_FLOATS]
@@ -179,6 +186,8 @@ int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, vo
  *                reference's lookup (pyviz/apap.py:209), first > last = no canvas column; row_extent alike
  *   cell_fast  : float [grid_rows*grid_cols][APAP_HINV_ROW] (out)
  */
+int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_raw, const int *counts, int batch,
+                 int n_points, int n_kp_padded, double scale, float *kp_table, void *stream);
 int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream);
 int apap_warp_tables(const float *cell_hinv, const int *col_extent, const int *row_extent, int grid_rows,
                      int grid_cols, int off_x, int off_y, int src_w, int src_h, float *cell_fast, void *stream);

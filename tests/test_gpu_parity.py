@@ -225,6 +225,32 @@ def test_device_kp_blocks_equal_host_restatement(n_kp):
         assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("n_kp", [1, 5, 128, 1000, 2049])
+def test_device_kp_rows_equal_host_restatement(n_kp):
+    """apap_kp_rows builds the keypoint row table on the device from the conditioned points: same bits as
+    build_kp_table on the reference's DLT matrix, ragged batch (the second scene has fewer matches) included."""
+    import torch
+    sc = synth.make_scene("mini", n_kp=max(n_kp, 4), mesh=4)
+    st = _stitcher(sc)
+    src, dst = sc.src[:n_kp], sc.dst[:n_kp]
+    short = max(1, n_kp // 3)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    scenes = [(src, dst), (src[:short] * np.float32(0.75), dst[:short])]
+    points = np.zeros((3, 2, n_kp, 2), dtype=np.float32)
+    for b, (s_, d_) in enumerate(scenes):
+        cf1, cf2, _ = st._condition(s_, d_)
+        points[0, b, :len(s_)], points[1, b, :len(s_)], points[2, b, :len(s_)] = cf1, cf2, s_
+    counts = torch.tensor([n_kp, short], dtype=torch.int32, device=dev)
+    got = st.kp_rows_device(torch.from_numpy(points).to(dev), counts).cpu().numpy()
+    for b, (s_, d_) in enumerate(scenes):
+        want, _ = st._prepare(s_, d_)
+        assert got.shape[1] >= want.shape[0]
+        assert np.array_equal(got[b, :want.shape[0]].view(np.uint32), want.view(np.uint32))
+        assert not got[b, want.shape[0]:].any()
+    one = st.kp_rows_device(torch.from_numpy(points[:, :1].copy()).to(dev)).cpu().numpy()      # counts = NULL
+    assert np.array_equal(one[0].view(np.uint32), got[0].view(np.uint32))
+
+
 def test_device_warp_tables_equal_host_restatement():
     """apap_warp_tables builds the fast-path records on the device: same bits as build_warp_tables (whose
     guard-band logic the CPU tests check), on a real grid and on degenerate / adversarial cells."""
