@@ -91,9 +91,10 @@ def spectral_segment_device(src_pts, dst_pts, diag, affinity_eps, device=None, r
     d_dev = rt.to_device(torch, device, np.ascontiguousarray(dst_pts, dtype=np.float32))
     g_dev = rt.to_device(torch, device, np.ascontiguousarray(diag, dtype=np.float64))
     m = torch.empty((n, n), dtype=torch.float64, device=device)
-    x = torch.full((n,), 1.0 / np.sqrt(n), dtype=torch.float64, device=device)
-    y = torch.empty_like(x)
-    norm_sq = torch.zeros(1, dtype=torch.float64, device=device)
+    y = torch.empty((2, n), dtype=torch.float64, device=device)              # ping-pong iterates
+    y[0].fill_(1.0 / np.sqrt(n))
+    norms = torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64, device=device)   # ring of |y_k|^2
+    x = torch.empty(n, dtype=torch.float64, device=device)
     diff = torch.zeros(1, dtype=torch.int64, device=device)     # bits of a non-negative double
     iters = 0
     with torch.cuda.device(device):
@@ -101,11 +102,8 @@ def spectral_segment_device(src_pts, dst_pts, diag, affinity_eps, device=None, r
         rt.check(lib.apap_affinity_matrix(s_dev.data_ptr(), d_dev.data_ptr(), g_dev.data_ptr(), n, float(rcp_value),
                                           m.data_ptr(), st), "apap_affinity_matrix")
         while iters < POWER_MAX_ITER:
-            for k in range(POWER_CHECK_EVERY):
-                if k == POWER_CHECK_EVERY - 1:
-                    diff.zero_()                                  # the test looks at the last step of the group
-                rt.check(lib.apap_power_step(m.data_ptr(), n, x.data_ptr(), y.data_ptr(), norm_sq.data_ptr(),
-                                             diff.data_ptr(), st), "apap_power_step")
+            rt.check(lib.apap_power_iterate(m.data_ptr(), n, y.data_ptr(), norms.data_ptr(), iters, POWER_CHECK_EVERY,
+                                            x.data_ptr(), diff.data_ptr(), st), "apap_power_iterate")
             iters += POWER_CHECK_EVERY
             if diff.view(torch.float64).item() <= POWER_TOL:
                 break

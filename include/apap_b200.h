@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 11
+#define APAP_ABI_VERSION 12
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -213,14 +213,17 @@ int apap_warp_perspective(const uint8_t *src, int src_h, int src_w, const double
  * apap_affinity_matrix: M [n][n] float64 (device): M[i][i] = diag[i] (match score + epipolar term, :104-111, computed
  *   by the caller), M[i][j] = max(4.5 - ((|s_i - s_j|^2 - |d_i - d_j|^2)^2) * rcp_value, 0) in numpy's float32
  *   arithmetic (:112-118); src_pts / dst_pts: float [n][2] (device), rcp_value = 1 / (2 affinity_eps^2).
- * apap_power_step: one step of the power iteration that replaces np.linalg.svd(M) + |U[:, 0]| (:122-123):
- *   y = M x, x <- y / |y|; *max_diff_bits is raised (atomic max on the bits of a non-negative double) to
- *   max_i |x_new[i] - x_old[i]|, for the caller's convergence test.  x, y: double [n]; norm_sq: double [1] scratch.
+ * apap_power_iterate: `steps` steps of the power iteration that replaces np.linalg.svd(M) + |U[:, 0]| (:122-123),
+ *   y_{k+1} = M (y_k / |y_k|), one kernel per step, then x = y / |y| of the last iterate and *max_diff_bits = the bits of
+ *   max_i |x[i] - x_before[i]| (x_before = the normalised iterate one step earlier) for the caller's convergence test.
+ *   y: double [2][n] ping-pong, iterate k lives in y[k & 1]; norms: double [3] ring, |y_k|^2 in norms[k % 3].  Before
+ *   the first call (first_step = 0) the caller stores a positive start vector in y[0], its squared norm in norms[0]
+ *   and zero in norms[1]; later calls pass first_step = the number of steps already done.
  */
 int apap_affinity_matrix(const float *src_pts, const float *dst_pts, const double *diag, int n, float rcp_value,
                          double *m, void *stream);
-int apap_power_step(const double *m, int n, double *x, double *y, double *norm_sq,
-                    unsigned long long *max_diff_bits, void *stream);
+int apap_power_iterate(const double *m, int n, double *y, double *norms, int first_step, int steps, double *x,
+                       unsigned long long *max_diff_bits, void *stream);
 
 /*
  * Panorama assembly of a sharded pass without an all-gather: broadcast `bytes` of device memory at `src` (this

@@ -33,11 +33,12 @@ def gw(mode):
 for _ in range(iters):
     p.gram(); p.eig()                                   # K1, K2 one by one
     p.dlt()                                             # K1 + K2 as the public call launches them (K2 overlapped)
+    p.st.kp_rows_device(p.points)                       # k_kp_rows
     p.st.kp_table_device(p.rows)                        # k_kp_blocks
     p.prepare_warp()                                    # k_warp_prep (+ uploads)
     p.warp(False); p.warp(True); p.blend()
     gw(0); gw(1); gw(2)                                 # k_warp_global: warp only, paste, mean blend
     if _ == 0:
-        psm.spectral_segment_device(sp_c, sp_o, sp_diag, 30.0, device=dev)   # k_affinity, k_matvec, k_rescale
+        psm.spectral_segment_device(sp_c, sp_o, sp_diag, 30.0, device=dev)   # k_affinity, k_power_step, k_power_diff
 torch.cuda.synchronize()
 print("profile pass ok", name, iters)
