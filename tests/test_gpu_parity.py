@@ -654,3 +654,24 @@ def test_errors_surface_as_exceptions():
     lib = rt.load_library()
     assert lib.apap_blend(None, None, None, 10, None) != 0
     assert b"null" in lib.apap_last_error()
+
+
+def test_integration_md_ctypes_stub_runs_and_matches():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer (raw C ABI, no cvx_proj_b200 host layer) is executed
+    as written and gives the same H grid as the package's own call, bit for bit."""
+    import os
+    import re
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes, math.*?)```", text, re.S).group(1)
+    block = block.replace('ctypes.CDLL("libapap_b200.so")', f'ctypes.CDLL({rt.LIB_PATH!r})')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    sc = synth.make_scene("mini")
+    st = _stitcher(sc)
+    st.local_homography_stub = types.MethodType(ns["local_homography"], st)
+    got, _ = st.local_homography_stub(sc.src, sc.dst, sc.vertices)
+    want, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

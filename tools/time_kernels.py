@@ -34,7 +34,7 @@ def _gwarp_setup():
 
 
 _gw = _gwarp_setup() if any(w.startswith("gwarp") for w in what) else None
-ops = {"gwarp": lambda: _gw(0), "gwarp_paste": lambda: _gw(1), "gwarp_mean": lambda: _gw(2), "gram": p.gram, "eig": p.eig, "warp": lambda: p.warp(False), "fused": lambda: p.warp(True), "blend": p.blend}
+ops = {"gwarp": lambda: _gw(0), "gwarp_paste": lambda: _gw(1), "gwarp_mean": lambda: _gw(2), "gram": p.gram, "eig": p.eig, "dlt": p.dlt, "warp": lambda: p.warp(False), "fused": lambda: p.warp(True), "blend": p.blend}
 res = {}
 for w in what:
     ts = []
