@@ -54,7 +54,7 @@ __device__ __forceinline__ void exact_coords(const GlobalWarpParams &p, int x, i
 // Fast path.  Inside one OpenCV block the map is v(x1) = 32 (a + b x1) / (c + d x1) per coordinate, so with an
 // anchor column xa:  v(xa + t) = v(xa) + K t / (Wa + d t),  K = 32 (b c - a d) / Wa,  Wa = c + d xa  (exact algebra).
 // Per 32-pixel segment of a canvas row one thread evaluates the anchor (its middle column) in float64 exactly as
-// OpenCV does -- 32 segments per warp instruction, so the slow FP64 pipe of the B200 is touched once per 32 pixels
+// OpenCV does -- 32 segments per warp instruction, so the FP64 pipe (half the FP32 rate, long dependent chains) is touched once per 32 pixels
 // instead of ~50 times per pixel -- and the pixels add the small term K t / (Wa + d t), |t| <= 16, in float32.  eps
 // bounds the float32 error of that term; a pixel whose sum lands within eps of a rounding boundary (x.5) is
 // re-decided with the float64 formula, the others round to the same integer in both arithmetics.
