@@ -96,6 +96,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// TMA 1-D bulk copy shared -> global (bulk async-group completion).
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {      // the shared source may be reused / released afterwards
+  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {     // generic-proxy shared writes -> visible to the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

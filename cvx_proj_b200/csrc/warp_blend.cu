@@ -321,12 +321,110 @@ __global__ void __launch_bounds__(kWarpThreads, APAP_WARP_CTAS) k_warp(const War
 // 16 pixels = 48 B = three 16-byte vectors per thread and per image.
 constexpr int kBlendThreads = 256;
 
-__device__ __forceinline__ uint32_t get_byte(const uint32_t (&w)[12], int o) { return (w[o >> 2] >> ((o & 3) * 8)) & 0xffu; }
+// Four pixels = 12 bytes = three words (w0, w1, w2).  One byte per pixel: the OR of its three channel bytes.
+__device__ __forceinline__ uint32_t pixel_or4(uint32_t w0, uint32_t w1, uint32_t w2) {
+  const uint32_t x = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);   // bytes 0, 3, 6, 9
+  const uint32_t y = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);   // bytes 1, 4, 7, 10
+  const uint32_t z = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);   // bytes 2, 5, 8, 11
+  return x | y | z;
+}
+// msb of every byte = that byte of v is non-zero (the other bits are junk)
+__device__ __forceinline__ uint32_t byte_nonzero_msb(uint32_t v) { return ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v; }
+// prmt.b32 with sign replication: selector nibble 8 + i gives 0xff / 0x00 from the msb of byte i
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(d) : "r"(a), "r"(sel));
+  return d;
+}
 
-__global__ void __launch_bounds__(kBlendThreads) k_blend(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
-                                                          uint4 *__restrict__ out, long long n_vec3,
-                                                          const uint8_t *__restrict__ a8, const uint8_t *__restrict__ b8,
-                                                          uint8_t *__restrict__ out8, long long n_px) {
+// uniform_blend of 16 pixels = 12 words per image, all in 32-bit SIMD, four pixels = three words at a time.
+__device__ __forceinline__ void blend16(const uint32_t (&wa)[12], const uint32_t (&wb)[12], uint32_t (&wo)[12]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t *pa = wa + 3 * g, *pb = wb + 3 * g;
+    // one flag per pixel: non-black in BOTH images
+    const uint32_t both = byte_nonzero_msb(pixel_or4(pa[0], pa[1], pa[2])) &
+                          byte_nonzero_msb(pixel_or4(pb[0], pb[1], pb[2]));       // msb of byte k: pixel k
+    const uint32_t m[3] = {prmt(both, 0x9888), prmt(both, 0xaa99), prmt(both, 0xbbba)};   // 0xff per byte of a flagged pixel
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const uint32_t x = pa[w], y = pb[w];
+      const uint32_t avg = (x & y) + (((x ^ y) & 0xfefefefeu) >> 1);   // per-byte (a + b) >> 1
+      wo[3 * g + w] = (avg & m[w]) | ((x | y) & ~m[w]);                 // else a + b, one of them being 0
+    }
+  }
+}
+
+// the last n_px % 16 pixels, one thread
+__device__ __forceinline__ void blend_tail(const uint8_t *__restrict__ a8, const uint8_t *__restrict__ b8,
+                                           uint8_t *__restrict__ out8, long long px0, long long n_px) {
+  for (long long px = px0; px < n_px; ++px) {
+    const uint8_t *pa = a8 + px * 3, *pb = b8 + px * 3;
+    const bool both = (pa[0] | pa[1] | pa[2]) && (pb[0] | pb[1] | pb[2]);
+    for (int c = 0; c < 3; ++c) {
+      const unsigned s = (unsigned)pa[c] + pb[c];
+      out8[px * 3 + c] = (uint8_t)(both ? (s >> 1) : s);
+    }
+  }
+}
+
+#ifndef APAP_BLEND_TMA
+#define APAP_BLEND_TMA 1         // 0 (lab): every thread loads and stores its own 48 bytes straight from / to global memory
+#endif
+
+// CTA = 256 units of 16 pixels = 12 KB per image.  One thread moves the CTA's slice of both images into shared memory
+// with two TMA bulk copies and the result back with one (whole 128-byte lines on the wire, no per-thread address
+// arithmetic); the threads read their 48 bytes as three LDS.128 (stride 48 B: conflict-free per quarter warp) and
+// write the result over their own slice of `a`.
+struct BlendSmem {
+  uint4 a[kBlendThreads * 3];
+  uint4 b[kBlendThreads * 3];
+  uint64_t bar;
+};
+
+__global__ void __launch_bounds__(kBlendThreads) k_blend(const uint8_t *__restrict__ a8, const uint8_t *__restrict__ b8,
+                                                          uint8_t *__restrict__ out8, long long n_vec3, long long n_px) {
+#if APAP_BLEND_TMA
+  __shared__ __align__(128) BlendSmem sm;
+  const long long unit0 = (long long)blockIdx.x * kBlendThreads;
+  const long long left = n_vec3 - unit0;
+  const int units = left >= kBlendThreads ? kBlendThreads : (left > 0 ? (int)left : 0);
+  const uint32_t bytes = (uint32_t)units * 48u;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    mbar_fence_init();
+    if (units > 0) {
+      mbar_arrive_expect_tx(&sm.bar, 2 * bytes);
+      bulk_g2s(sm.a, a8 + unit0 * 48, bytes, &sm.bar);
+      bulk_g2s(sm.b, b8 + unit0 * 48, bytes, &sm.bar);
+    }
+  }
+  __syncthreads();
+  if (units > 0) mbar_wait(&sm.bar, 0);
+  if (tid < units) {
+    uint32_t wa[12], wb[12], wo[12];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const uint4 x = sm.a[tid * 3 + v], y = sm.b[tid * 3 + v];
+      wa[4 * v + 0] = x.x; wa[4 * v + 1] = x.y; wa[4 * v + 2] = x.z; wa[4 * v + 3] = x.w;
+      wb[4 * v + 0] = y.x; wb[4 * v + 1] = y.y; wb[4 * v + 2] = y.z; wb[4 * v + 3] = y.w;
+    }
+    blend16(wa, wb, wo);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) sm.a[tid * 3 + v] = make_uint4(wo[4 * v], wo[4 * v + 1], wo[4 * v + 2], wo[4 * v + 3]);
+    fence_proxy_async_smem();
+  } else if (tid == units) {
+    if (left < kBlendThreads) blend_tail(a8, b8, out8, n_vec3 * 16, n_px);     // only in the CTA that holds the end
+  }
+  __syncthreads();
+  if (tid == 0 && units > 0) {
+    bulk_s2g(out8 + unit0 * 48, sm.a, bytes);
+    bulk_commit_wait_read();
+  }
+#else
+  const uint4 *a = reinterpret_cast<const uint4 *>(a8), *b = reinterpret_cast<const uint4 *>(b8);
+  uint4 *out = reinterpret_cast<uint4 *>(out8);
   const long long gid = (long long)blockIdx.x * kBlendThreads + threadIdx.x;
   if (gid < n_vec3) {
     uint32_t wa[12], wb[12], wo[12];
@@ -337,39 +435,14 @@ __global__ void __launch_bounds__(kBlendThreads) k_blend(const uint4 *__restrict
       wa[4 * v + 0] = x.x; wa[4 * v + 1] = x.y; wa[4 * v + 2] = x.z; wa[4 * v + 3] = x.w;
       wb[4 * v + 0] = y.x; wb[4 * v + 1] = y.y; wb[4 * v + 2] = y.z; wb[4 * v + 3] = y.w;
     }
-    // per-byte mask: 0xff where the byte's pixel is non-black in BOTH images
-    uint32_t both[12];
-#pragma unroll
-    for (int w = 0; w < 12; ++w) both[w] = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const uint32_t na = get_byte(wa, 3 * k) | get_byte(wa, 3 * k + 1) | get_byte(wa, 3 * k + 2);
-      const uint32_t nb = get_byte(wb, 3 * k) | get_byte(wb, 3 * k + 1) | get_byte(wb, 3 * k + 2);
-      if (na != 0 && nb != 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) both[(3 * k + c) >> 2] |= 0xffu << (((3 * k + c) & 3) * 8);
-      }
-    }
-#pragma unroll
-    for (int w = 0; w < 12; ++w) {
-      const uint32_t avg = __vhaddu4(wa[w], wb[w]);     // per-byte (a + b) >> 1
-      const uint32_t sum = __vadd4(wa[w], wb[w]);       // per-byte a + b (one of them is 0)
-      wo[w] = (avg & both[w]) | (sum & ~both[w]);
-    }
+    blend16(wa, wb, wo);
 #pragma unroll
     for (int v = 0; v < 3; ++v)
       __stcs(out + gid * 3 + v, make_uint4(wo[4 * v], wo[4 * v + 1], wo[4 * v + 2], wo[4 * v + 3]));
   } else if (gid == n_vec3) {
-    // tail: fewer than 16 pixels
-    for (long long px = n_vec3 * 16; px < n_px; ++px) {
-      const uint8_t *pa = a8 + px * 3, *pb = b8 + px * 3;
-      const bool both = (pa[0] | pa[1] | pa[2]) && (pb[0] | pb[1] | pb[2]);
-      for (int c = 0; c < 3; ++c) {
-        const unsigned s = (unsigned)pa[c] + pb[c];
-        out8[px * 3 + c] = (uint8_t)(both ? (s >> 1) : s);
-      }
-    }
+    blend_tail(a8, b8, out8, n_vec3 * 16, n_px);
   }
+#endif
 }
 
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
@@ -426,10 +499,7 @@ int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, 
   const long long threads = n_vec3 + 1;   // +1 thread for the tail
   const long long blocks = (threads + kBlendThreads - 1) / kBlendThreads;
   if (blocks > 2147483647LL) return fail(APAP_E_TOOBIG, "blend: image too large");
-  k_blend<<<(unsigned)blocks, kBlendThreads, 0, st>>>(reinterpret_cast<const uint4 *>(a),
-                                                      reinterpret_cast<const uint4 *>(b),
-                                                      reinterpret_cast<uint4 *>(out), n_vec3, a, b, out,
-                                                      (long long)n_px);
+  k_blend<<<(unsigned)blocks, kBlendThreads, 0, st>>>(a, b, out, n_vec3, (long long)n_px);
   return check_cuda(cudaGetLastError(), "k_blend launch");
 }
 
