@@ -535,6 +535,13 @@ def test_uniform_blend_golden_and_tails(golden):
         a[rng.random((hh, ww)) < 0.3] = 0
         b[rng.random((hh, ww)) < 0.3] = 0
         assert np.array_equal(apap_utils.uniform_blend(a, b), orc.uniform_blend(a, b)), (hh, ww)
+    # channel values from the corners of the byte arithmetic (pixels with some channels zero, carries, msb), and pixel
+    # counts at and around whole CTAs of the kernel (256 units of 16 pixels)
+    palette = np.array([0, 0, 1, 0x7f, 0x80, 0xfe, 0xff], dtype=np.uint8)
+    for hh, ww in ((7, 33), (64, 64), (1, 4096 + 5), (3, 4096), (257, 16)):
+        a = palette[rng.integers(0, palette.size, size=(hh, ww, 3))]
+        b = palette[rng.integers(0, palette.size, size=(hh, ww, 3))]
+        assert np.array_equal(apap_utils.uniform_blend(a, b), orc.uniform_blend(a, b)), (hh, ww)
 
 
 def test_uniform_blend_full_size_properties():

@@ -429,3 +429,52 @@ def test_spectral_host_pieces_vs_oracle(golden):
         diag = psm.affinity_diagonal(c, o, cf, of, fmat, OPTS["epi_weight"])
         want = np.diag(so.affinity_matrix(c, o, cf, of, fmat, OPTS["epi_weight"], OPTS["affinity_eps"]))
         assert np.array_equal(diag, want)
+
+
+def _prmt(a, b, sel):
+    """PTX ``prmt.b32 d, a, b, sel`` (default mode) on uint32 arrays: nibble i of ``sel`` picks byte (nibble & 7)
+    of the pair (a = bytes 0-3, b = bytes 4-7); nibble bit 3 replicates the picked byte's sign bit over the byte."""
+    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
+    pair = a | (b << np.uint64(32))
+    out = np.zeros_like(a)
+    for i in range(4):
+        nib = (sel >> (4 * i)) & 0xF
+        byte = (pair >> np.uint64(8 * (nib & 7))) & np.uint64(0xFF)
+        if nib & 8:
+            byte = np.where(byte & np.uint64(0x80), np.uint64(0xFF), np.uint64(0))
+        out |= byte << np.uint64(8 * i)
+    return out.astype(np.uint32)
+
+
+def test_blend_simd_word_arithmetic_equals_uniform_blend():
+    """The 32-bit SIMD formulation of ``k_blend`` (csrc/warp_blend.cu ``blend16``: PRMT gathers of the channel bytes,
+    carry-trick non-zero test, sign-replicating PRMT to spread the pixel flag, per-byte floor average), restated in
+    numpy on four pixels = three words, equals uniform_blend (pyviz/apap_utils.py:75-88) for every byte pattern class."""
+    rng = np.random.default_rng(11)
+    palette = np.array([0, 0, 0, 1, 0x7F, 0x80, 0xFE, 0xFF], dtype=np.uint8)
+    a = np.concatenate([palette[rng.integers(0, 8, size=(20000, 4, 3))],
+                        rng.integers(0, 256, size=(20000, 4, 3), dtype=np.uint8)])
+    b = np.concatenate([palette[rng.integers(0, 8, size=(20000, 4, 3))],
+                        rng.integers(0, 256, size=(20000, 4, 3), dtype=np.uint8)])
+    b = b[rng.permutation(b.shape[0])]
+    wa = np.ascontiguousarray(a).reshape(-1, 12).view("<u4")          # [n, 3] words of 4 pixels
+    wb = np.ascontiguousarray(b).reshape(-1, 12).view("<u4")
+
+    def pixel_or4(w):
+        x = _prmt(_prmt(w[:, 0], w[:, 1], 0x0630), w[:, 2], 0x5210)
+        y = _prmt(_prmt(w[:, 0], w[:, 1], 0x0741), w[:, 2], 0x6210)
+        z = _prmt(_prmt(w[:, 0], w[:, 1], 0x0052), w[:, 2], 0x7410)
+        return x | y | z
+
+    def nonzero_msb(v):
+        return (((v & np.uint32(0x7F7F7F7F)).astype(np.uint64) + 0x7F7F7F7F).astype(np.uint32)) | v
+
+    both = nonzero_msb(pixel_or4(wa)) & nonzero_msb(pixel_or4(wb))
+    out = np.empty_like(wa)
+    for w, sel in enumerate((0x9888, 0xAA99, 0xBBBA)):
+        m = _prmt(both, both, sel)
+        x, y = wa[:, w], wb[:, w]
+        avg = ((x & y).astype(np.uint64) + (((x ^ y) & np.uint32(0xFEFEFEFE)) >> np.uint32(1))).astype(np.uint32)
+        out[:, w] = (avg & m) | ((x | y) & ~m)
+    got = out.view(np.uint8).reshape(-1, 4, 3)
+    assert np.array_equal(got, orc.uniform_blend(a, b))
