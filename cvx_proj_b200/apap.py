@@ -168,6 +168,68 @@ def invert_grid_inplace(local_homography: np.ndarray) -> None:
     local_homography[...] = np.linalg.inv(local_homography)
 
 
+def invert_grid_certified(grid: np.ndarray):
+    """Host restatement of ``apap_invert_grid`` (tests): float64 partial-pivoting inverse of every float32 3x3 cell,
+    rounded to float32, and the certificate that the rounding equals numpy's (``np.linalg.inv`` = LAPACK ``dgesv``
+    on the float64 promotion + one rounding).  Both float64 results lie within ``E = c u |X| (P^T |L||U|) |X|`` of
+    the exact inverse (componentwise forward error of a GEPP solve, ``c = 64`` for ``3n = 9``), so an entry ``x``
+    with no float32 rounding boundary inside ``[x - 2E, x + 2E]`` rounds the same way in both.  Flagged (left to
+    numpy): entries near a boundary, (near-)ties in the pivot search, zero / tiny / huge / non-finite entries,
+    singular cells.  Returns ``(inverse float32 [cells, 3, 3], flags bool [cells])``."""
+    a = np.asarray(grid, dtype=np.float32).reshape(-1, 3, 3).astype(np.float64)
+    n = a.shape[0]
+    lu = a.copy()
+    perm = np.tile(np.arange(3), (n, 1))
+    flag = np.zeros(n, dtype=bool)
+    rows = np.arange(n)
+    with np.errstate(all="ignore"):
+        for k in range(2):
+            col = np.abs(lu[:, k:, k])
+            piv = k + np.argmax(col, axis=1)                     # first maximum, like idamax
+            best = col[rows, piv - k]
+            near = col >= (best * (1.0 - 1e-9))[:, None]
+            flag |= near.sum(axis=1) > 1
+            flag |= ~(best > 0.0) | ~np.isfinite(best)
+            swap = lu[rows, piv].copy()
+            lu[rows, piv] = lu[:, k]
+            lu[:, k] = swap
+            pk = perm[rows, piv].copy()
+            perm[rows, piv] = perm[:, k]
+            perm[:, k] = pk
+            pivot = np.where(flag & (lu[:, k, k] == 0.0), 1.0, lu[:, k, k])
+            for i in range(k + 1, 3):
+                l = lu[:, i, k] / pivot
+                lu[:, i, k] = l
+                for j in range(k + 1, 3):
+                    lu[:, i, j] -= l * lu[:, k, j]
+        bad = ~(np.abs(lu[:, 2, 2]) > 0.0) | ~np.isfinite(lu[:, 2, 2])
+        flag |= bad
+        lu[bad, 2, 2] = 1.0
+        x = np.empty((n, 3, 3))
+        for j in range(3):
+            b = (perm == j).astype(np.float64)
+            y0 = b[:, 0]
+            y1 = b[:, 1] - lu[:, 1, 0] * y0
+            y2 = b[:, 2] - lu[:, 2, 0] * y0 - lu[:, 2, 1] * y1
+            x2 = y2 / lu[:, 2, 2]
+            x1 = (y1 - lu[:, 1, 2] * x2) / lu[:, 1, 1]
+            x0 = (y0 - lu[:, 0, 1] * x1 - lu[:, 0, 2] * x2) / lu[:, 0, 0]
+            x[:, 0, j], x[:, 1, j], x[:, 2, j] = x0, x1, x2
+        lower = np.abs(np.tril(lu, -1)) + np.eye(3)
+        upper = np.abs(np.triu(lu))
+        m = lower @ upper                                         # |L||U| of P A
+        w = np.empty_like(m)
+        w[rows[:, None], perm] = m                                # rows back in A's order
+        ax = np.abs(x)
+        e = 2.0 * 64.0 * 2.0 ** -53 * (ax @ (w @ ax))
+        f = x.astype(np.float32)
+        lo = 0.5 * (f.astype(np.float64) + np.nextafter(f, np.float32(-np.inf)).astype(np.float64))
+        hi = 0.5 * (f.astype(np.float64) + np.nextafter(f, np.float32(np.inf)).astype(np.float64))
+        ok = (ax > 1e-30) & (ax < 1e30) & np.isfinite(e) & (x - e > lo) & (x + e < hi)
+        flag |= ~ok.all(axis=(1, 2))
+    return f, flag
+
+
 def _cell_extent(lut: np.ndarray, n: int):
     """Per cell index: smallest / largest pixel coordinate mapped to it (lo > hi = unused)."""
     lo = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
@@ -751,6 +813,36 @@ class APAP:
                 1 if multicast_ptr is not None else 0, rt.stream_ptr(torch, device)), "apap_warp")
         return out
 
+    def invert_grid(self, local_homography, device=None) -> int:
+        """The per-cell ``np.linalg.inv`` of ``local_warp`` (pyviz/apap.py:201-203), stored back into the caller's
+        array, with the same bits as numpy's.  The GPU inverts every cell in float64 (``apap_invert_grid``) and
+        certifies the cells whose float32 rounding cannot differ from numpy's (LAPACK ``dgesv`` + one rounding);
+        the rest -- about 1 in 10^4 on homography grids, and every singular or degenerate cell -- go through
+        ``np.linalg.inv`` itself here, so errors surface exactly as in the reference (``LinAlgError``).
+        Returns the number of cells numpy inverted.  Grids that are not C-contiguous float32 take numpy throughout."""
+        grid = local_homography
+        if not (isinstance(grid, np.ndarray) and grid.dtype == np.float32 and grid.flags.c_contiguous
+                and grid.ndim >= 2 and grid.shape[-2:] == (3, 3)) or grid.size == 0:
+            invert_grid_inplace(grid)
+            return int(grid.size // 9)
+        torch, device = rt.torch_cuda(device if device is not None else self.device)
+        lib = rt.load_library()
+        cells = grid.size // 9
+        flat = grid.reshape(cells, 3, 3)
+        with torch.cuda.device(device):
+            g_dev = rt.to_device(torch, device, grid)
+            out_dev = torch.empty(cells * 9, dtype=torch.float32, device=device)
+            flag_dev = torch.empty(cells, dtype=torch.uint8, device=device)
+            rt.check(lib.apap_invert_grid(g_dev.data_ptr(), cells, out_dev.data_ptr(), flag_dev.data_ptr(),
+                                          rt.stream_ptr(torch, device)), "apap_invert_grid")
+            out = rt.to_host(torch, out_dev)
+            redo = np.flatnonzero(rt.to_host(torch, flag_dev))
+        fixed = np.linalg.inv(flat[redo]) if redo.size else None      # before anything is overwritten; may raise
+        flat[...] = out.reshape(cells, 3, 3)
+        if redo.size:
+            flat[redo] = fixed
+        return int(redo.size)
+
     def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False):
         mesh_n, pt_size, _, _ = local_homography.shape
         ori_h, ori_w, _ = ori_img.shape
@@ -763,7 +855,7 @@ class APAP:
             centre_dev = (centre_img.contiguous() if not isinstance(centre_img, np.ndarray)
                           else rt.to_device(torch, device, centre_img.astype(np.uint8, copy=False)))
         # in-place per-cell inverse, stored back in the caller's array (pyviz/apap.py:201-203)
-        invert_grid_inplace(local_homography)
+        self.invert_grid(local_homography, device)
         col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
         tables = self.warp_tables_device(local_homography, col_cell, row_cell, ori_w, ori_h, device)
         out = self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)

@@ -1,11 +1,11 @@
 // Input preparation that used to run in numpy on the host and dominated the end-to-end time of the
-// public calls (measured at c2: ~6 ms of table building against a 33 us warp kernel; the per-cell inverse of
-// pyviz/apap.py:201-203 stays numpy's own LAPACK call on the host -- its float32 results are the float64 dgesv
-// of OpenBLAS rounded once, and no other arithmetic reproduces every bit of them):
+// public calls (measured at c2: ~6 ms of table building and 10 ms of per-cell numpy inverses against a 33 us warp
+// kernel):
 //   k_kp_rows     conditioned keypoint pairs -> keypoint row table  (host restatement: apap.build_kp_table)
 //   k_kp_blocks   keypoint row table -> tensor-core block table (host restatement: apap.build_kp_blocks)
 //   k_warp_prep   per-cell fast-path records of the mesh warp   (host restatement: apap.build_warp_tables)
-// The kernels reproduce their numpy restatements bit for bit (explicit _rn arithmetic, no FMA
+//   k_inv_grid    the per-cell inverse of local_warp, accepted only where it provably rounds like numpy's
+// The first three reproduce their numpy restatements bit for bit (explicit _rn arithmetic, no FMA
 // contraction, same operation order), so the CPU tests of the guard band cover the device-built tables.
 #include <math.h>
 
@@ -220,6 +220,121 @@ int launch_warp_prep(const float *inv_h, const int *col_ext, const int *row_ext,
   return check_cuda(cudaGetLastError(), "k_warp_prep launch");
 }
 
+// ------------------------------------------------------------------------------------ k_inv_grid
+// The per-cell inverse of local_warp (pyviz/apap.py:201-203).  The reference's float32 result is numpy's:
+// LAPACK dgesv on the float64 promotion (Gaussian elimination with partial pivoting), rounded to float32 once.
+// One thread per cell does the same factorisation in float64 and rounds; because the two float64 results may differ
+// in their last bits (operation order, FMA), the cell is only accepted when every entry is provably far from a
+// float32 rounding boundary: both results lie within  E = c u |X| (P^T |L||U|) |X|  of the exact inverse (the
+// componentwise forward error of a GEPP solve, Higham, Accuracy and Stability of Numerical Algorithms, Thm 9.4,
+// with c = 64 in place of 3n = 9), so if [x - 2E, x + 2E] contains no midpoint between adjacent float32 numbers,
+// round(x) = round(dgesv's x).  Everything else -- an entry near a boundary, a (near-)tie in the pivot search (the
+// other factorisation could pivot differently), zero / tiny / huge / non-finite entries, singular cells -- is
+// flagged and left to the host, which calls numpy on those cells (~1 in 10^4 on homography grids).
+__global__ void __launch_bounds__(128) k_inv_grid(const float *__restrict__ h, int cells, float *__restrict__ out,
+                                                   unsigned char *__restrict__ flags) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= cells) return;
+  double lu[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) lu[i][j] = (double)h[(size_t)cell * 9 + i * 3 + j];
+  int perm[3] = {0, 1, 2};
+  bool flag = false;
+  constexpr double kTie = 1.0 - 1e-9;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    int piv = k;
+    double best = fabs(lu[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i) {
+      const double v = fabs(lu[i][k]);
+      if (v > best) { best = v; piv = i; }
+    }
+#pragma unroll
+    for (int i = k; i < 3; ++i)
+      if (i != piv && fabs(lu[i][k]) >= best * kTie) flag = true;          // (near-)tie: pivot order not certain
+    if (!(best > 0.0) || !isfinite(best)) { flag = true; best = 1.0; }
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i) {
+      if (i == piv) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const double t = lu[k][j]; lu[k][j] = lu[i][j]; lu[i][j] = t; }
+        const int t = perm[k]; perm[k] = perm[i]; perm[i] = t;
+      }
+    }
+    const double pivot = flag && lu[k][k] == 0.0 ? 1.0 : lu[k][k];
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i) {
+      const double l = lu[i][k] / pivot;
+      lu[i][k] = l;
+#pragma unroll
+      for (int j = k + 1; j < 3; ++j) lu[i][j] -= l * lu[k][j];
+    }
+  }
+  if (!(fabs(lu[2][2]) > 0.0) || !isfinite(lu[2][2])) { flag = true; lu[2][2] = 1.0; }
+  // X = U^-1 L^-1 P
+  double x[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double b0 = perm[0] == j ? 1.0 : 0.0, b1 = perm[1] == j ? 1.0 : 0.0, b2 = perm[2] == j ? 1.0 : 0.0;
+    const double y0 = b0, y1 = b1 - lu[1][0] * y0, y2 = b2 - lu[2][0] * y0 - lu[2][1] * y1;
+    const double x2 = y2 / lu[2][2];
+    const double x1 = (y1 - lu[1][2] * x2) / lu[1][1];
+    const double x0 = (y0 - lu[0][1] * x1 - lu[0][2] * x2) / lu[0][0];
+    x[0][j] = x0; x[1][j] = x1; x[2][j] = x2;
+  }
+  // W = P^T |L||U| (rows back in A's order), then E = c u |X| W |X|
+  double w[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double m = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double l = k < i ? fabs(lu[i][k]) : (k == i ? 1.0 : 0.0);
+        const double u = k <= j ? fabs(lu[k][j]) : 0.0;
+        m += l * u;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (perm[i] == r) w[r][j] = m;
+    }
+  double wx[3][3];                                  // W |X|
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      wx[i][j] = w[i][0] * fabs(x[0][j]) + w[i][1] * fabs(x[1][j]) + w[i][2] * fabs(x[2][j]);
+  constexpr double kCu = 64.0 * 1.1102230246251565e-16;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double v = x[i][j];
+      const double e = 2.0 * kCu * (fabs(x[i][0]) * wx[0][j] + fabs(x[i][1]) * wx[1][j] + fabs(x[i][2]) * wx[2][j]);
+      const float f = (float)v;
+      const double av = fabs(v);
+      if (!(av > 1e-30) || !(av < 1e30) || !isfinite(e)) {
+        flag = true;
+      } else {
+        const double lo = 0.5 * ((double)f + (double)nextafterf(f, -INFINITY));
+        const double hi = 0.5 * ((double)f + (double)nextafterf(f, INFINITY));
+        if (!(v - e > lo) || !(v + e < hi)) flag = true;
+      }
+      out[(size_t)cell * 9 + i * 3 + j] = f;
+    }
+  flags[cell] = flag ? 1 : 0;
+}
+
+int launch_inv_grid(const float *h, int cells, float *out, unsigned char *flags, cudaStream_t st) {
+  if (cells == 0) return 0;
+  k_inv_grid<<<(cells + 127) / 128, 128, 0, st>>>(h, cells, out, flags);
+  return check_cuda(cudaGetLastError(), "k_inv_grid launch");
+}
+
 }  // namespace apap
 
 using namespace apap;
@@ -243,6 +358,11 @@ int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_
   if (!kp_table || !kp_blocks) return fail(APAP_E_BADARG, "null pointer");
   if (batch <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "kp_blocks: bad sizes");
   return launch_kp_blocks(kp_table, batch, n_kp_padded, kp_blocks, static_cast<cudaStream_t>(stream));
+}
+
+int apap_invert_grid(const float *grid, int cells, float *grid_inv, unsigned char *flags, void *stream) {
+  if (!grid || !grid_inv || !flags || cells < 0) return fail(APAP_E_BADARG, "invert_grid: bad arguments");
+  return launch_inv_grid(grid, cells, grid_inv, flags, static_cast<cudaStream_t>(stream));
 }
 
 int apap_warp_tables(const float *cell_hinv, const int *col_extent, const int *row_extent, int grid_rows, int grid_cols,

@@ -165,8 +165,7 @@ class ShardedAPAP:
 
         st, s = self.stitcher, self.me
         torch, device = rt.torch_cuda(st.device)
-        from .apap import invert_grid_inplace
-        invert_grid_inplace(local_h_rows)
+        st.invert_grid(local_h_rows, device)
         full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
         full[...] = np.eye(3, dtype=np.float32)
         full[s.cell_row0:s.cell_row1] = local_h_rows
@@ -184,11 +183,10 @@ class ShardedAPAP:
         warp kernel's own stores instead of a broadcast kernel -- one kernel, but its 96-byte row fragments use the
         links 2.5x worse); returns this rank's (complete) panorama tensor."""
         from . import _runtime as rt
-        from .apap import invert_grid_inplace
 
         st, s = self.stitcher, self.me
         torch, device = rt.torch_cuda(st.device)
-        invert_grid_inplace(local_h_rows)
+        st.invert_grid(local_h_rows, device)
         full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
         full[...] = np.eye(3, dtype=np.float32)
         full[s.cell_row0:s.cell_row1] = local_h_rows

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 12
+#define APAP_ABI_VERSION 13
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -186,6 +186,16 @@ int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, vo
  *                reference's lookup (pyviz/apap.py:209), first > last = no canvas column; row_extent alike
  *   cell_fast  : float [grid_rows*grid_cols][APAP_HINV_ROW] (out)
  */
+/*
+ * apap_invert_grid: the per-cell inverse of APAP.local_warp, pyviz/apap.py:201-203 (np.linalg.inv of every float32
+ * 3x3 cell = LAPACK dgesv on the float64 promotion, rounded once).  grid_inv gets the float64 partial-pivoting inverse
+ * rounded to float32; flags[c] = 0 where that is PROVABLY the float32 numpy returns (every entry farther from a
+ * float32 rounding boundary than twice the forward-error bound of the solve, no pivot ties, no zero / tiny / huge /
+ * non-finite entries), 1 where the caller must invert the cell with numpy / LAPACK itself (singular cells included).
+ *   grid, grid_inv : float [cells][9] (device);  flags : uint8 [cells] (device)
+ */
+int apap_invert_grid(const float *grid, int cells, float *grid_inv, unsigned char *flags, void *stream);
+
 int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_raw, const int *counts, int batch,
                  int n_points, int n_kp_padded, double scale, float *kp_table, void *stream);
 int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream);

@@ -682,3 +682,43 @@ def test_integration_md_ctypes_stub_runs_and_matches():
     want, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
     assert got.shape == want.shape
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_device_invert_grid_has_numpys_bits():
+    """APAP.invert_grid (GPU float64 inverse + certificate, numpy for the uncertified cells) leaves exactly the bits of
+    the reference's per-cell np.linalg.inv (pyviz/apap.py:201-203) in the caller's array: a real grid, two million
+    homography-like cells of mixed conditioning (a plain float64 LU rounds ~1 in 10^6 entries differently),
+    affine cells (exact zeros), NaN cells, a float64 grid; singular cells raise like numpy."""
+    sc = synth.make_scene("c2")
+    st = _stitcher(sc)
+    h, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    want = np.linalg.inv(h)
+    redo = st.invert_grid(h)
+    assert np.array_equal(h.view(np.uint32), want.view(np.uint32))
+    print(f"invert_grid c2: {redo} of {h.size // 9} cells went through numpy")
+    assert redo < 0.01 * h.size / 9
+
+    rng = np.random.default_rng(17)
+    n = 2_000_000
+    g = np.tile(np.eye(3), (n, 1, 1))
+    g[:, :2, :2] += rng.normal(0, 0.2, (n, 2, 2))
+    g[:, :2, 2] = rng.normal(0, 1, (n, 2)) * 10.0 ** rng.uniform(0, 3.7, (n, 1))
+    g[:, 2, :2] = rng.normal(0, 1, (n, 2)) * 10.0 ** rng.uniform(-7, -3, (n, 1))
+    g *= 10.0 ** rng.uniform(-2, 2, (n, 1, 1))
+    g = g.astype(np.float32)
+    g[::1000, 2, :2] = 0                                    # affine cells: exact zeros in the inverse
+    g[5] = np.nan
+    want = np.linalg.inv(g)
+    redo = st.invert_grid(g)
+    same = g.view(np.uint32) == want.view(np.uint32)
+    print(f"invert_grid stress: {redo} of {n} cells through numpy, {int((~same).sum())} differing entries")
+    assert same.all()
+    assert redo < 0.02 * n
+
+    g64 = np.linalg.inv(want[100:200].astype(np.float64))
+    want64 = np.linalg.inv(g64)
+    assert st.invert_grid(g64) == 100 and np.array_equal(g64, want64)            # not float32: numpy throughout
+    bad = np.tile(np.eye(3, dtype=np.float32), (4, 1, 1))
+    bad[2] = 0
+    with pytest.raises(np.linalg.LinAlgError):
+        st.invert_grid(bad)

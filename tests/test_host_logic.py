@@ -297,7 +297,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 12
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 13
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 
@@ -478,3 +478,36 @@ def test_blend_simd_word_arithmetic_equals_uniform_blend():
         out[:, w] = (avg & m) | ((x | y) & ~m)
     got = out.view(np.uint8).reshape(-1, 4, 3)
     assert np.array_equal(got, orc.uniform_blend(a, b))
+
+
+def test_certified_inverse_restatement_has_numpys_bits():
+    """``invert_grid_certified`` (numpy restatement of ``apap_invert_grid``): every cell it certifies carries exactly
+    the float32 bits of ``np.linalg.inv`` (pyviz/apap.py:201-203); degenerate classes are never certified; on
+    homography-like grids almost every cell is certified."""
+    rng = np.random.default_rng(23)
+    n = 200_000
+    g = np.tile(np.eye(3), (n, 1, 1))
+    g[:, :2, :2] += rng.normal(0, 0.2, (n, 2, 2))
+    g[:, :2, 2] = rng.normal(0, 1, (n, 2)) * 10.0 ** rng.uniform(0, 3.7, (n, 1))
+    g[:, 2, :2] = rng.normal(0, 1, (n, 2)) * 10.0 ** rng.uniform(-7, -3, (n, 1))
+    g *= 10.0 ** rng.uniform(-2, 2, (n, 1, 1))
+    g = g.astype(np.float32)
+    g[::1000, 2, :2] = 0                                    # affine: exact zeros in the inverse
+    g[7] = np.nan
+    g[11] = 0                                               # singular
+    g[13, 1] = g[13, 0]                                     # singular, rank 2
+    g[17, 1, 0] = g[17, 0, 0]                               # tie in the first pivot search
+    f, flag = papap.invert_grid_certified(g)
+    assert flag[[0, 1000, 7, 11, 13, 17]].all()
+    keep = ~flag
+    want = np.linalg.inv(g[keep])
+    assert np.array_equal(f[keep].view(np.uint32), want.view(np.uint32))
+    assert flag.mean() < 0.005
+    # an ill-conditioned family: the certificate gives up instead of guessing
+    ill = np.tile(np.eye(3, dtype=np.float32), (1000, 1, 1))
+    ill[:, 0, 1] = 1.0
+    ill[:, 1, 1] = (1.0 + rng.uniform(1e-7, 1e-6, 1000)).astype(np.float32)
+    ill[:, 1, 0] = 1.0
+    f, flag = papap.invert_grid_certified(ill)
+    want = np.linalg.inv(ill[~flag])
+    assert np.array_equal(f[~flag].view(np.uint32), want.view(np.uint32))
