@@ -433,13 +433,13 @@ def run_ours(args):
         if k >= W:
             e2e_dlt.append(t1 - t0)
             e2e_warp.append(t2 - t1)
-    launches += 6 * K          # k_kp_rows, k_kp_blocks, k_gram_tc, k_eig; k_warp_prep, k_warp
+    launches += 7 * K          # k_kp_rows, k_kp_blocks, k_gram_tc, k_eig; k_inv_grid, k_warp_prep, k_warp
     e2e_dlt_s = max_over_ranks(float(np.mean(e2e_dlt)))
     e2e_warp_s = max_over_ranks(float(np.mean(e2e_warp)))
     h2d_dlt = 3 * sc.src.shape[0] * 8 + 4 + p.cells * 8 + 144     # conditioned pairs + raw points, count, anchors, matrices
     d2h_dlt = p.cells * 36
-    h2d_warp = 3 * src_px + p.cells * 36 + 8 * sc.final_w + 8 * p.tables.n_blocks + 16 * sc.mesh_cells
-    d2h_warp = 3 * canvas_px
+    h2d_warp = 3 * src_px + 2 * p.cells * 36 + 8 * sc.final_w + 8 * p.tables.n_blocks + 16 * sc.mesh_cells   # grid up twice: to invert, inverted
+    d2h_warp = 3 * canvas_px + p.cells * 37                      # canvas + the inverted grid and its flags
 
     # ---- c3 strong-scaled across ranks (cell rows + row bands, one all-gather) -----------------
     c3 = None
@@ -524,7 +524,7 @@ def run_ours(args):
             "e2e": {"value": world * canvas_px / e2e_warp_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_warp,
                     "d2h_bytes_per_step": d2h_warp, "ms_per_step": e2e_warp_s * 1e3,
                     "call": "APAP.local_warp(img, H, mesh) with a pinned numpy image, numpy canvas out "
-                            "(includes the host per-cell np.linalg.inv the reference also does)"},
+                            "(includes the in-place per-cell inverse of pyviz/apap.py:201-203: certified GPU inverse, numpy for the cells it flags)"},
             "exact_path_cells_frac": p.flagged_cells,
         },
         "global_warp": {

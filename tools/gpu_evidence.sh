@@ -11,6 +11,6 @@ python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json
 python tools/profile_pass.py c2 2 > $out/pp_plain_$tag.log 2>&1; echo "profile_pass rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $out/launches_$tag.csv \
     python tools/profile_pass.py c2 2 > $out/ncu_list_$tag.log 2>&1; echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_eig|k_warp|k_blend|k_kp_rows|k_kp_blocks|k_affinity|k_power_step|k_power_diff' -c 24 \
+ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_eig|k_warp|k_blend|k_kp_rows|k_kp_blocks|k_inv_grid|k_affinity|k_power_step|k_power_diff' -c 26 \
     -o $out/prof_$tag -f python tools/profile_pass.py c2 1 > $out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
 head -c 1500 $out/bench_$tag.json

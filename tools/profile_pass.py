@@ -35,6 +35,7 @@ for _ in range(iters):
     p.dlt()                                             # K1 + K2 as the public call launches them (K2 overlapped)
     p.st.kp_rows_device(p.points)                       # k_kp_rows
     p.st.kp_table_device(p.rows)                        # k_kp_blocks
+    p.st.invert_grid(p.h_out.cpu().numpy().reshape(-1, 3, 3))   # k_inv_grid (+ copies)
     p.prepare_warp()                                    # k_warp_prep (+ uploads)
     p.warp(False); p.warp(True); p.blend()
     gw(0); gw(1); gw(2)                                 # k_warp_global: warp only, paste, mean blend
