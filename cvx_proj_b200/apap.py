@@ -5,13 +5,13 @@ same method names, argument meaning, return layout and side effects -- over the 
 ``libapap_b200.so`` (``include/apap_b200.h``).  What runs where:
 
   host (numpy, bit-identical to the reference, O(N) or O(cells)):
-      getNormalize2DPts / getConditionerFromPts / point_normalize / matrix_generate
-      (pyviz/apap.py:35-119), the per-cell ``np.linalg.inv`` of ``local_warp``
-      (pyviz/apap.py:201-203), the cell lookup tables (pyviz/apap.py:207,209)
+      getNormalize2DPts / getConditionerFromPts / point_normalize (pyviz/apap.py:35-100),
+      the cell lookup tables (pyviz/apap.py:207,209), ``np.linalg.inv`` for the few cells whose
+      GPU inverse is not certified to round like numpy's (``APAP.invert_grid``)
   GPU (hand-written sm_100a kernels, no CPU fallback):
-      K1 weights + Gram contraction, K2 9x9 Jacobi + de-normalisation
-      (pyviz/apap.py:147-168), K3 mesh warp (pyviz/apap.py:206-215),
-      K4 uniform_blend (pyviz/apap_utils.py:75-88), local_weight (pyviz/apap.py:150-153)
+      the keypoint tables (pyviz/apap.py:103-119), K1 weights + Gram contraction, K2 9x9 eigenvector +
+      de-normalisation (pyviz/apap.py:147-168), the per-cell inverse (pyviz/apap.py:201-203), K3 mesh warp
+      (pyviz/apap.py:206-215), K4 uniform_blend (pyviz/apap_utils.py:75-88), local_weight (pyviz/apap.py:150-153)
 
 Inputs and outputs are host numpy arrays by default, exactly like the reference; passing a
 CUDA ``torch`` tensor as the image keeps the result on the device (opt-in).
@@ -164,7 +164,8 @@ def invert_grid_inplace(local_homography: np.ndarray) -> None:
     """The per-cell ``np.linalg.inv`` of ``local_warp`` (pyviz/apap.py:201-203), stored back into the
     caller's array: one stacked call = the same LAPACK routine per 3x3 block as the reference's loop
     (bit-identical, tests/test_oracle_golden.py).  Not threaded: numpy's gufunc holds the GIL here
-    (measured on the GPU box: 11 ms serial vs 28 ms on the pool at 40 000 cells)."""
+    (measured on the GPU box: 11 ms serial vs 28 ms on the pool at 40 000 cells).  ``APAP.invert_grid`` is what
+    the product calls: the GPU inverse for the cells it can certify, this routine's numpy call for the rest."""
     local_homography[...] = np.linalg.inv(local_homography)
 
 
@@ -848,7 +849,7 @@ class APAP:
         ori_h, ori_w, _ = ori_img.shape
         on_device = not isinstance(ori_img, np.ndarray)
         torch, device = rt.torch_cuda(ori_img.device if on_device else self.device)
-        # the image copies go first: they run (asynchronously, from pinned memory) under the host's LAPACK loop
+        # the image copies go first: they are asynchronous from pinned memory
         src_dev = ori_img.contiguous() if on_device else rt.to_device(torch, device, ori_img.astype(np.uint8, copy=False))
         centre_dev = None
         if centre_img is not None:
