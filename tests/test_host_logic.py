@@ -511,3 +511,30 @@ def test_certified_inverse_restatement_has_numpys_bits():
     f, flag = papap.invert_grid_certified(ill)
     want = np.linalg.inv(ill[~flag])
     assert np.array_equal(f[~flag].view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("family", ["uniform", "row_scales", "col_scales", "near_rank1", "small_ints", "hilbert"])
+def test_certified_inverse_never_certifies_a_different_rounding(family):
+    """The certificate of ``invert_grid_certified`` over matrix families far from homographies: whatever it certifies
+    has numpy's bits; what it cannot decide it flags (near-singular, exact zeros, pivot ties)."""
+    rng = np.random.default_rng(31)
+    n = 30000
+    if family == "uniform":
+        g = rng.uniform(-1, 1, (n, 3, 3))
+    elif family == "row_scales":
+        g = rng.normal(0, 1, (n, 3, 3)) * 10.0 ** rng.uniform(-6, 6, (n, 3, 1))
+    elif family == "col_scales":
+        g = rng.normal(0, 1, (n, 3, 3)) * 10.0 ** rng.uniform(-6, 6, (n, 1, 3))
+    elif family == "near_rank1":
+        g = rng.normal(0, 1, (n, 3, 1)) * rng.normal(0, 1, (n, 1, 3)) + 10.0 ** rng.uniform(-7, -3, (n, 1, 1)) * rng.normal(0, 1, (n, 3, 3))
+    elif family == "small_ints":
+        g = rng.integers(-3, 4, (n, 3, 3)).astype(np.float64)
+    else:
+        g = (1.0 / (np.arange(3)[:, None] + np.arange(3)[None, :] + 1.0))[None] * (1 + 1e-3 * rng.normal(0, 1, (n, 3, 3)))
+    g = g.astype(np.float32)
+    f, flag = papap.invert_grid_certified(g)
+    keep = ~flag
+    want = np.linalg.inv(g[keep])                            # numpy never raises on a certified cell
+    assert np.array_equal(f[keep].view(np.uint32), want.view(np.uint32))
+    if family in ("uniform", "row_scales", "col_scales", "hilbert"):
+        assert flag.mean() < 0.01
