@@ -715,6 +715,23 @@ def test_device_invert_grid_has_numpys_bits():
     assert same.all()
     assert redo < 0.02 * n
 
+    # families far from homographies: what the device certifies still has numpy's bits, the rest goes through numpy
+    m = 200_000
+    families = {
+        "uniform": rng.uniform(-1, 1, (m, 3, 3)),
+        "row scales": rng.normal(0, 1, (m, 3, 3)) * 10.0 ** rng.uniform(-6, 6, (m, 3, 1)),
+        "near rank 1": rng.normal(0, 1, (m, 3, 1)) * rng.normal(0, 1, (m, 1, 3))
+        + 10.0 ** rng.uniform(-7, -3, (m, 1, 1)) * rng.normal(0, 1, (m, 3, 3)),
+        "small integers": rng.integers(-3, 4, (m, 3, 3)).astype(np.float64) + 4 * np.eye(3),
+    }
+    for name, fam in families.items():
+        fam = fam.astype(np.float32)
+        fam = fam[np.abs(np.linalg.det(fam.astype(np.float64))) > 1e-30]       # numpy itself raises on singular cells
+        want_f = np.linalg.inv(fam)
+        redo_f = st.invert_grid(fam)
+        print(f"invert_grid {name}: {redo_f} of {len(fam)} cells through numpy")
+        assert np.array_equal(fam.view(np.uint32), want_f.view(np.uint32)), name
+
     g64 = np.linalg.inv(want[100:200].astype(np.float64))
     want64 = np.linalg.inv(g64)
     assert st.invert_grid(g64) == 100 and np.array_equal(g64, want64)            # not float32: numpy throughout
