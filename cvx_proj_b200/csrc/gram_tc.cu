@@ -336,9 +336,13 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
       for (int e = 0; e < kStepKb; ++e) {
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; k += 2) {               // lo = w - hi (exact), two at a time on the packed FP32x2 adder
           hi[k] = tf32_head(w[8 * e + k]);
-          lo[k] = __float_as_uint(w[8 * e + k] - __uint_as_float(hi[k]));
+          hi[k + 1] = tf32_head(w[8 * e + k + 1]);
+          const float2 l = __fadd2_rn(make_float2(w[8 * e + k], w[8 * e + k + 1]),
+                                      make_float2(-__uint_as_float(hi[k]), -__uint_as_float(hi[k + 1])));
+          lo[k] = __float_as_uint(l.x);
+          lo[k + 1] = __float_as_uint(l.y);
         }
         tmem_st8(slot + e * 16, hi);
         tmem_st8(slot + e * 16 + 8, lo);
