@@ -433,6 +433,7 @@ class WarpTables(NamedTuple):
     cell_fast: object       # float32 [cells * 12]
     cell_hinv: object       # float32 [cells * 9]
     col_lut: object         # int32 [canvas_w * 2]
+    col_extent: object      # int32 [grid_cols * 2]
     row_blocks: object      # int32 [n_blocks * 2]
     n_blocks: int
     row0: int               # the band of canvas rows the blocks cover
@@ -787,15 +788,17 @@ class APAP:
             rt.check(lib.apap_warp_tables(hinv_dev.data_ptr(), views[3].data_ptr(), views[4].data_ptr(), gr, gc,
                                           int(self.offset_x), int(self.offset_y), int(src_w), int(src_h),
                                           fast.data_ptr(), rt.stream_ptr(torch, device)), "apap_warp_tables")
-        return WarpTables(fast, hinv_dev, views[1].view(torch.int32), views[2].view(torch.int32),
-                          int(blocks.shape[0]), int(row0), int(row1))
+        return WarpTables(fast, hinv_dev, views[1].view(torch.int32), views[3].view(torch.int32),
+                          views[2].view(torch.int32), int(blocks.shape[0]), int(row0), int(row1))
 
-    def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False, multicast_ptr=None):
+    def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False, multicast_ptr=None,
+                    legacy=False):
         """Device-resident K3 (optionally fused with K4): writes the canvas rows ``[tables.row0,
         tables.row1)`` into ``out`` (``[row1-row0, final_width, 3]`` uint8, allocated when None).
         ``multicast_ptr``: address of canvas row ``tables.row0`` inside an NVLS multicast mapping of a panorama buffer
         that every GPU of the group holds (``sharding.SymmetricPanorama``): the band is stored into all of them by
-        the kernel itself and ``out`` is not written."""
+        the kernel itself and ``out`` is not written.  ``legacy``: round 1's strip kernel instead of the tile engine
+        (A/B timing and tests; same bytes)."""
         torch, device = rt.torch_cuda(src_dev.device)
         lib = rt.load_library()
         fw = int(self.final_width)
@@ -806,11 +809,12 @@ class APAP:
         with torch.cuda.device(device):
             rt.check(lib.apap_warp(
                 src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
-                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.row_blocks.data_ptr(),
-                tables.n_blocks, grid_cols, fw, int(self.offset_x), int(self.offset_y), tables.row0,
-                centre_dev.data_ptr() if centre_dev is not None else None, ch, cw,
+                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.col_extent.data_ptr(),
+                tables.row_blocks.data_ptr(), tables.n_blocks, grid_cols, fw, int(self.offset_x), int(self.offset_y),
+                tables.row0, tables.row1, centre_dev.data_ptr() if centre_dev is not None else None, ch, cw,
                 int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
-                n_bytes if multicast_ptr is not None else out.numel(), int(force_exact),
+                n_bytes if multicast_ptr is not None else out.numel(),
+                (rt.WARP_FORCE_EXACT if force_exact else 0) | (rt.WARP_LEGACY if legacy else 0),
                 1 if multicast_ptr is not None else 0, rt.stream_ptr(torch, device)), "apap_warp")
         return out
 

@@ -109,15 +109,20 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 }
 
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-              const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w,
-              int off_x, int off_y, int row0, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
-              size_t out_band_bytes, int force_exact, int multicast, void *stream) {
+              const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks, int grid_cols,
+              int canvas_w, int off_x, int off_y, int row0, int row1, const uint8_t *centre, int centre_h,
+              int centre_w, uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *stream) {
   if (!src || !cell_fast || !cell_hinv || !col_lut || !out_band) return fail(APAP_E_BADARG, "null pointer");
+  if (!col_extent && !(flags & APAP_WARP_LEGACY)) return fail(APAP_E_BADARG, "warp: null col_extent");
+  if (flags & ~(APAP_WARP_FORCE_EXACT | APAP_WARP_LEGACY)) return fail(APAP_E_BADARG, "warp: unknown flag");
   if (n_blocks < 0 || (n_blocks > 0 && !row_blocks)) return fail(APAP_E_BADARG, "warp: bad row blocks");
   if (src_h <= 0 || src_w <= 0 || canvas_w <= 0 || grid_cols <= 0) return fail(APAP_E_BADARG, "warp: sizes must be > 0");
   if (centre && (centre_h <= 0 || centre_w <= 0)) return fail(APAP_E_BADARG, "warp: bad centre image size");
-  return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, row_blocks, n_blocks, grid_cols, canvas_w, off_x,
-                     off_y, row0, centre, centre_h, centre_w, out_band, out_band_bytes, force_exact,
+  if (row0 < 0 || row1 < row0) return fail(APAP_E_BADARG, "warp: bad row band");
+  if (out_band_bytes < (size_t)(row1 - row0) * (size_t)canvas_w * 3)
+    return fail(APAP_E_BADARG, "warp: out_band is smaller than the rows [row0, row1) of the canvas");
+  return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, col_extent, row_blocks, n_blocks, grid_cols,
+                     canvas_w, off_x, off_y, row0, centre, centre_h, centre_w, out_band, out_band_bytes, flags,
                      multicast, static_cast<cudaStream_t>(stream));
 }
 

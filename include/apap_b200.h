@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 13
+#define APAP_ABI_VERSION 14
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -135,28 +135,39 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
  *               path, g > 1 = the whole cell maps outside the source image and is left black
  *   cell_hinv : float [grid_rows*grid_cols][9], the inverted grid of pyviz/apap.py:201-203
  *   col_lut   : uint32 [canvas_w][2] = {cell column, float32 bits of dx}
+ *   col_extent: int32 [grid_cols][2] = {first, last} canvas column of the cell column (the array apap_warp_tables
+ *               takes); the tile engine bounds a tile's source footprint with it (unused by APAP_WARP_LEGACY)
  *   row_blocks: uint32 [n_blocks][2] = {first canvas row | rows << 28 (rows = 1..APAP_WARP_BLOCK_ROWS),
- *               cell row | dy of the first row << 16}, in canvas order; a block never crosses a cell
- *               row; the blocks passed are the rows that get written (a row band of a sharded run =
- *               its blocks); canvas rows < 2^28, cell rows and dy < 2^16
- *   row0      : canvas row stored at out_band[0]
- *   out_band  : uint8 [rows][canvas_w][3], out_band_bytes < 2 GiB; when it is 4-byte aligned and
- *               canvas_w % 4 == 0 the kernel uses packed 32-bit stores
+ *               cell row | dy of the first row << 16}, in canvas order and contiguous (block k+1 starts at or
+ *               before the row after block k's last); a block never crosses a cell row; the blocks passed are
+ *               the rows that get written (a row band of a sharded run = its blocks); canvas rows < 2^28, cell
+ *               rows and dy < 2^16
+ *   row0, row1: out_band holds the canvas rows [row0, row1); every row block lies inside
+ *   out_band  : uint8 [row1 - row0][canvas_w][3], out_band_bytes >= that and < 2 GiB.  Rows leave the kernel as
+ *               TMA bulk stores when the band is 16-byte aligned and canvas_w % 16 == 0, as 32-bit stores when
+ *               4-byte aligned and canvas_w % 4 == 0, else as byte stores
  *   centre    : optional uint8 [centre_h][centre_w][3] pasted at (off_x, off_y) and blended with
  *               the warped pixel by the uniform_blend rule (fused K3+K4, pyviz/apap.py:259-261);
  *               NULL = plain warp
- *   force_exact : non-zero = every pixel takes the float64 path (validation switch)
+ *   flags     : APAP_WARP_FORCE_EXACT = every pixel takes the float64 path (validation switch);
+ *               APAP_WARP_LEGACY = the strip kernel of round 1 (one warp per 32 columns, gathers from global
+ *               memory, shuffle re-pack) instead of the tile engine (csrc/warp_tile.cu: the source footprint of
+ *               a 128 x 32 canvas tile staged in shared memory with TMA bulk copies, LDS gathers, the output
+ *               tile assembled in shared memory and stored as whole row segments).  Same bytes either way.
  *   multicast   : non-zero = out_band is an NVLS multicast address (one mapping of the same panorama buffer on every
  *                 GPU of the group, e.g. torch symmetric memory's multicast_ptr + band offset): the kernel stores with
  *                 multimem.st, so the NVSwitch writes this rank's row band into every GPU's panorama -- the panorama
- *                 is assembled by the warp itself, no all-gather.  Stores are 16 bytes wide: needs canvas_w % 16 == 0 and a
- *                 16-byte aligned band; the caller synchronises the group afterwards.
+ *                 is assembled by the warp itself, no all-gather.  Stores are 16 bytes wide, whole 384-byte tile rows
+ *                 (tile engine): needs canvas_w % 16 == 0 and a 16-byte aligned band; the caller synchronises the
+ *                 group afterwards.
  */
+#define APAP_WARP_FORCE_EXACT 1
+#define APAP_WARP_LEGACY      2
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-              const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols,
-              int canvas_w, int off_x, int off_y, int row0,
+              const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks,
+              int grid_cols, int canvas_w, int off_x, int off_y, int row0, int row1,
               const uint8_t *centre, int centre_h, int centre_w,
-              uint8_t *out_band, size_t out_band_bytes, int force_exact, int multicast, void *stream);
+              uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *stream);
 
 /*
  * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,

@@ -372,6 +372,82 @@ def test_local_warp_c2_full_size_vs_oracle():
     assert diff.size == 0, f"{diff.size} pixels differ, first {diff[:5]}"
 
 
+def _device_warp(st, sc, img, inv, centre=None, legacy=False, rows=None):
+    """K3 through warp_tables_device + warp_device on cuda tensors (``legacy`` = round 1's strip kernel)."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gr, gc = inv.shape[0], inv.shape[1]
+    col, row = cell_lookup_tables(sc.mesh, sc.final_w, sc.final_h, gr, gc)
+    r0, r1 = rows if rows is not None else (0, sc.final_h)
+    tabs = st.warp_tables_device(inv, col, row, img.shape[1], img.shape[0], dev, r0, r1)
+    out = st.warp_device(torch.from_numpy(img).to(dev), tabs, gc, legacy=legacy,
+                         centre_dev=torch.from_numpy(centre).to(dev) if centre is not None else None)
+    return out.cpu().numpy()
+
+
+def test_tile_engine_equals_legacy_strip_kernel_c2():
+    """The tile engine (TMA-staged source boxes, LDS gathers, bulk row stores) and round 1's strip kernel pick the same
+    bytes on the full c2 canvas, plain and fused with the blend, and on a row band that starts mid-cell-row."""
+    sc = synth.make_scene("c2")
+    img = sc.image(1)
+    centre = synth.make_image(sc.width, sc.height, seed=2)
+    st = _stitcher(sc)
+    h, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+    inv = orc.invert_grid(h)
+    a = _device_warp(st, sc, img, inv)
+    b = _device_warp(st, sc, img, inv, legacy=True)
+    assert np.array_equal(a, b) and (a.max(axis=-1) > 0).mean() > 0.3
+    fa = _device_warp(st, sc, img, inv, centre=centre)
+    fb = _device_warp(st, sc, img, inv, centre=centre, legacy=True)
+    assert np.array_equal(fa, fb)
+    band = _device_warp(st, sc, img, inv, rows=(1001, 1777))
+    assert np.array_equal(band, a[1001:1777])
+
+
+@pytest.mark.parametrize("src_w,src_h,fw,fh,off", [(1000, 700, 1100, 800, (37, 21)),      # source rows not 16-byte aligned
+                                                    (1024, 768, 1196, 822, (90, 30)),      # canvas rows 4- but not 16-byte aligned
+                                                    (1024, 768, 1203, 811, (90, 30)),      # canvas rows not even 4-byte aligned
+                                                    (640, 240, 2048, 352, (300, 60))])     # many tiles across, few down
+def test_tile_engine_alignment_cases_vs_oracle(src_w, src_h, fw, fh, off):
+    rng = np.random.default_rng(src_w + fw)
+    img = rng.integers(1, 256, size=(src_h, src_w, 3), dtype=np.uint8)
+    centre = rng.integers(0, 256, size=(src_h, src_w, 3), dtype=np.uint8)
+    st = APAP(0.5, 100, [fw, fh], list(off))
+    mesh = apap_utils.get_mesh((fw, fh), 24)
+    yy, xx = np.meshgrid(np.arange(23), np.arange(23), indexing="ij")
+    h = np.tile(np.array([[1.02, 0.03, 12.0], [-0.02, 0.98, -4.5], [1e-5, -2e-5, 1]], np.float32), (23, 23, 1, 1))
+    h[..., 0, 2] += (3 * np.sin(xx / 4.0)).astype(np.float32)
+    h[..., 1, 2] += (2 * np.cos(yy / 5.0)).astype(np.float32)
+    want = orc.local_warp(img, orc.invert_grid(h), mesh, (fw, fh), off)
+    got = st.local_warp(img, h.copy(), mesh)
+    assert np.array_equal(got, want) and got.any()
+    pasted = orc.paste_centre(want, centre, off)
+    assert np.array_equal(st.local_warp_blend(img, h.copy(), mesh, centre), orc.uniform_blend(want, pasted))
+
+
+@pytest.mark.parametrize("kind", ["rot90", "rot30", "minify3", "magnify4", "flip"])
+def test_tile_engine_large_footprints_vs_oracle(kind):
+    """Maps whose source box per tile is tall, wide or huge (rotation, minification: the box may not fit shared memory
+    and the tile gathers from global memory), tiny (magnification) or mirrored."""
+    rng = np.random.default_rng(11)
+    sw, sh, fw, fh = 512, 384, 640, 416
+    img = rng.integers(1, 256, size=(sh, sw, 3), dtype=np.uint8)
+    c, s = np.cos(np.pi / 6), np.sin(np.pi / 6)
+    fwd = {"rot90": [[0, -1, fw - 100.3], [1, 0, 10.2], [0, 0, 1]],
+           "rot30": [[c, -s, 200.5], [s, c, -40.25], [1e-5, 0, 1]],
+           "minify3": [[1 / 3, 0, 50.1], [0, 1 / 3, 60.7], [0, 1e-5, 1]],
+           "magnify4": [[4, 0.1, -300.3], [0.05, 4, -200.9], [0, 0, 1]],
+           "flip": [[-1, 0, fw - 70.4], [0.01, 1, 3.3], [0, 0, 1]]}[kind]
+    h = np.tile(np.array(fwd, np.float32), (12, 12, 1, 1))
+    h[..., 0, 2] += rng.uniform(-2, 2, size=(12, 12)).astype(np.float32)
+    st = APAP(0.5, 100, [fw, fh], [0, 0])
+    mesh = apap_utils.get_mesh((fw, fh), 13)
+    want = orc.local_warp(img, orc.invert_grid(h), mesh, (fw, fh), (0, 0))
+    got = st.local_warp(img, h.copy(), mesh)
+    assert want.any() and np.array_equal(got, want)
+
+
+
 def _sampled_cells_vs_oracle(sc, h, step):
     """H grid on every `step`-th cell row / column against the float64 Gram oracle (the full grid is too much
     float64 work for the CPU at the BASELINE sizes; the GPU computed every cell)."""

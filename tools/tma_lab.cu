@@ -1,0 +1,94 @@
+// LAB: which 2-D tensor-map TMA load configurations run on this box (sm_100a)?
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/tma_lab tools/tma_lab.cu ; run: tools/tma_lab
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+struct Params { CUtensorMap maps[3]; int c0, c1, bytes, which; unsigned *out; };
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int kVariant>
+__global__ void k(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap single) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 32768);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const CUtensorMap *m = kVariant == 0 ? &single : &p.maps[p.which];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(p.bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(sm)),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(p.c0), "r"(p.c1), "r"(s32(bar))
+                 : "memory");
+  }
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(s32(bar)) : "memory");
+  }
+  unsigned sum = 0;
+  for (int i = threadIdx.x; i < p.bytes; i += blockDim.x) sum += sm[i];
+  atomicAdd(p.out, sum);
+}
+
+typedef CUresult (*Enc)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main(int argc, char **argv) {
+  const int only = argc > 1 ? atoi(argv[1]) : -1, only_variant = argc > 2 ? atoi(argv[2]) : -1;
+  void *fp = nullptr; cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
+  printf("entry point: %s q=%d ptr=%p\n", cudaGetErrorName(e), (int)q, fp);
+  Enc enc = (Enc)fp;
+  const int W = 1024, H = 768, pitch = W * 3;
+  std::vector<uint8_t> img((size_t)pitch * H);
+  for (size_t i = 0; i < img.size(); ++i) img[i] = (uint8_t)(1 + i % 251);
+  uint8_t *d; cudaMalloc(&d, img.size()); cudaMemcpy(d, img.data(), img.size(), cudaMemcpyHostToDevice);
+  unsigned *out; cudaMalloc(&out, 4);
+  struct Cfg { const char *name; CUtensorMapDataType dt; int esz; int bw, bh, c0, c1; } cfgs[] = {
+      {"u32 box 112x45 c0=32 (16B aligned)", CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, 112, 45, 32, 40},
+      {"u32 box 64x80 c0=33 (4B aligned)", CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, 64, 80, 33, 40},
+      {"u32 box 112x45 c0=-8 c1=-5", CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, 112, 45, -8, -5},
+      {"u32 box 32x160 past the end", CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, 32, 160, 760, 700},
+      {"u8 box 256x40 c0=48", CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 40, 48, 40},
+      {"u8 box 256x40 c0=33", CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 40, 33, 40},
+  };
+  for (int variant = 0; variant < 2; ++variant)
+    for (int ci = 0; ci < (int)(sizeof(cfgs) / sizeof(cfgs[0])); ++ci) {
+      if ((only >= 0 && ci != only) || (only_variant >= 0 && variant != only_variant)) continue;
+      auto &c = cfgs[ci];
+      Params p; memset(&p, 0, sizeof(p));
+      const cuuint64_t dims[2] = {(cuuint64_t)(pitch / c.esz), (cuuint64_t)H};
+      const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+      const cuuint32_t box[2] = {(cuuint32_t)c.bw, (cuuint32_t)c.bh};
+      const cuuint32_t ones[2] = {1, 1};
+      CUtensorMap m;
+      CUresult r = enc(&m, c.dt, 2, d, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p.maps[0] = p.maps[1] = p.maps[2] = m; p.which = 2;
+      p.c0 = c.c0; p.c1 = c.c1; p.bytes = c.bw * c.esz * c.bh; p.out = out;
+      cudaMemset(out, 0, 4);
+      if (variant == 0) { cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000); k<0><<<1, 128, 40000>>>(p, m); }
+      else { cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000); k<1><<<1, 128, 40000>>>(p, m); }
+      e = cudaDeviceSynchronize();
+      unsigned got = 0; cudaMemcpy(&got, out, 4, cudaMemcpyDeviceToHost);
+      // expected sum on the host (zero outside the image)
+      unsigned want = 0;
+      for (int r2 = 0; r2 < c.bh; ++r2)
+        for (int b = 0; b < c.bw * c.esz; ++b) {
+          long long y = c.c1 + r2, xb = (long long)c.c0 * c.esz + b;
+          if (y >= 0 && y < H && xb >= 0 && xb < pitch) want += img[(size_t)y * pitch + xb];
+        }
+      printf("variant %d (%s) %-34s encode=%d run=%s sum %u want %u %s\n", variant, variant ? "map inside struct" : "map as own param",
+             c.name, (int)r, cudaGetErrorName(e), got, want, got == want ? "OK" : "MISMATCH");
+      if (e != cudaSuccess) { printf("sticky error, stop\n"); return 1; }
+    }
+  return 0;
+}
