@@ -63,23 +63,32 @@ constexpr int kBoxShapes = 3;
 __host__ __device__ constexpr int box_w(int m) { return m == 0 ? 448 : m == 1 ? 256 : 128; }
 __host__ __device__ constexpr int box_h(int m) { return kBoxBytes / box_w(m) > 256 ? 256 : kBoxBytes / box_w(m); }
 
+constexpr int kRecRuns = 4;                               // cell rows of a tile whose records are staged ...
+constexpr int kRecCols = 16;                              // ... for at most this many cell columns (else global loads)
+
 struct TileInfo {                // what the producer tells the workers about a tile
   int x_lo, y_lo;                // first source pixel column / row of the staged box (kGlobal: 0, 0)
   int pitch;                     // bytes per staged row (kGlobal: pixels per image row)
   int shift;                     // byte offset of pixel x_lo inside a staged row
   int mode;
+  int r_first, n_rows;           // canvas rows of the tile
+  int c_lo;                      // first cell column of the tile
+  int rec_ok;                    // the cell records of the tile are staged in Stage::rec
   int pad[3];
+  uint2 blk[kTileBlocks];        // the tile's row block entries
+  int slot[kTileBlocks];         // cell-row run of every block = first index into Stage::rec
 };
 
 struct Stage {
   alignas(128) uint8_t box[kBoxBytes];
   alignas(16) uint8_t zero[16];
+  alignas(16) float4 rec[kRecRuns][kRecCols][3];          // fast-path records of the tile's cells
 };
 
 struct TileSmem {
   Stage st[2];
   alignas(128) uint8_t out[2][kOutBytes];
-  TileInfo info[2];
+  alignas(16) TileInfo info[2];
   alignas(8) uint64_t full[2];
   uint64_t empty[2];
 };
@@ -94,6 +103,7 @@ struct TileParams {
   int src_tma_ok;              // source rows 16-byte aligned and the maps encoded: boxes can be staged
   int store_mode;              // 0 bytes, 1 words, 2 TMA bulk rows, 3 multimem
   int tiles_x, n_tiles;
+  int step_x, step_y;          // gridDim.x = step_y * tiles_x + step_x: how a CTA's tile coordinates advance
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -137,7 +147,7 @@ __device__ __forceinline__ uint32_t centre_px(const WarpParams &p, int cx, int c
 template <bool kStaged, bool kFull, bool kBlend>
 __device__ __forceinline__ void tile_block(const WarpParams &p, const CellState &c, int pitch, int kbase,
                                            uint32_t guard_addr, uint8_t *__restrict__ orow, float dy0, int n_rows, int x,
-                                           int y0, bool col_ok) {
+                                           int y0, bool col_ok, int cell) {
   constexpr int P = kBlockRows;
   uint32_t so[P];                              // kStaged: shared-memory address; else pixel index / kNoPixel / kFlagPixel
   const uint32_t guard = kStaged ? guard_addr : kFlagPixel;
@@ -221,7 +231,7 @@ __device__ __forceinline__ void tile_block(const WarpParams &p, const CellState 
   // rare: the reference's float64 arithmetic, bytes from global memory
   bool any_guard = so[0] == guard || so[1] == guard || so[2] == guard || so[3] == guard;
   if (__any_sync(0xffffffffu, any_guard)) {
-    const float *hinv = p.cell_hinv + (size_t)c.cell * 9;
+    const float *hinv = p.cell_hinv + (size_t)cell * 9;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       if ((!kFull && k >= n_rows) || so[k] != guard) continue;
@@ -238,33 +248,52 @@ __device__ __forceinline__ void tile_block(const WarpParams &p, const CellState 
   }
 }
 
-// A worker warp's share of one tile: 32 columns x up to kWarpBlocks row blocks.
+// A worker warp's share of one tile: 32 columns x up to kWarpBlocks row blocks.  Block entries and (normally)
+// the cells' fast-path records come from shared memory, where the producer staged them.
 template <bool kStaged, bool kBlend>
-__device__ __forceinline__ void tile_warp_work(const WarpParams &p, const TileInfo &f, const uint8_t *__restrict__ box,
+__device__ __forceinline__ void tile_warp_work(const WarpParams &p, const TileInfo &f, const Stage &stg,
                                                uint8_t *__restrict__ out_tile, const uint2 cl, int x, bool col_ok,
-                                               int lane_col, int tb, int nb, int r_first) {
+                                               int lane_col, int b0, int nb) {
   const float dxf = __uint_as_float(cl.y);
-  const uint32_t box_addr = smem_u32(box);
+  const uint32_t box_addr = smem_u32(stg.box);
+  const int rec_col = (int)cl.x - f.c_lo;
   CellState c;
   c.b0 = c.b1 = c.b2 = c.m0 = c.m1 = 0.f; c.m2 = 1.f; c.hme = -1.f;
   c.qbx = c.qby = 0; c.cell_row = -1; c.cell = 0; c.outside = false;
   int kbase = 0;
 #pragma unroll 1
   for (int bi = 0; bi < nb; ++bi) {
-    const uint2 e = __ldg(p.row_blocks + tb + bi);
+    const uint2 e = f.blk[b0 + bi];
     const int i0 = (int)(e.x & 0x0fffffffu), n = (int)(e.x >> 28);
     const int cell_row = (int)(e.y & 0xffffu);
-    if (cell_row != c.cell_row) {               // warp-uniform
-      enter_cell_row(p, cl, dxf, cell_row, c);
+    if (cell_row != c.cell_row) {               // warp-uniform: the strip enters a new cell row
+      c.cell_row = cell_row;
+      float4 u, v, w;
+      if (f.rec_ok) {
+        const float4 *rec = stg.rec[f.slot[b0 + bi]][rec_col];
+        u = rec[0]; v = rec[1]; w = rec[2];
+      } else {
+        const float4 *rec = p.cell_fast + (size_t)(cell_row * p.grid_cols + (int)cl.x) * 3;
+        u = __ldg(rec); v = __ldg(rec + 1); w = __ldg(rec + 2);
+      }
+      c.m0 = fmaf(u.x, dxf, u.z); c.b0 = u.y;
+      c.m1 = fmaf(u.w, dxf, v.y); c.b1 = v.x;
+      c.m2 = fmaf(v.z, dxf, w.x); c.b2 = v.w;
+      c.qbx = __float_as_int(w.y);
+      c.qby = __float_as_int(w.z);
+      // g = 0.5 - eps; a record with g < 0 (degenerate cell, forced) never passes; NaN never passes
+      c.hme = p.force_exact ? -1.f : w.w;
+      c.outside = w.w > 1.f && !p.force_exact;
       // staged: address = box + (iy - y_lo) * pitch + (ix - x_lo) * 3 + shift, iy = ty_bits + qby, ix = tx_bits + qbx
       kbase = (int)box_addr + (c.qby - f.y_lo) * f.pitch + (c.qbx - f.x_lo) * 3 + f.shift;
     }
-    uint8_t *orow = out_tile + (uint32_t)(i0 - r_first) * kOutPitch + lane_col * 3;
+    uint8_t *orow = out_tile + (uint32_t)(i0 - f.r_first) * kOutPitch + lane_col * 3;
     const float dy0 = (float)(e.y >> 16);
+    const int cell = cell_row * p.grid_cols + (int)cl.x;
     if (n == kBlockRows)
-      tile_block<kStaged, true, kBlend>(p, c, f.pitch, kbase, box_addr + kFlagOff, orow, dy0, n, x, i0 - p.off_y, col_ok);
+      tile_block<kStaged, true, kBlend>(p, c, f.pitch, kbase, box_addr + kFlagOff, orow, dy0, n, x, i0 - p.off_y, col_ok, cell);
     else
-      tile_block<kStaged, false, kBlend>(p, c, f.pitch, kbase, box_addr + kFlagOff, orow, dy0, n, x, i0 - p.off_y, col_ok);
+      tile_block<kStaged, false, kBlend>(p, c, f.pitch, kbase, box_addr + kFlagOff, orow, dy0, n, x, i0 - p.off_y, col_ok, cell);
   }
 }
 
@@ -283,16 +312,22 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
   if (tid < 8) reinterpret_cast<uint32_t *>(sm.st[tid >> 2].zero)[tid & 3] = 0u;
   __syncthreads();
 
+  const int tiles_x = tp.tiles_x;
+  int txi = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;  // coordinates of this CTA's current tile
+
   if (warp == kWorkerWarps) {
     // =============================== producer warp ==================================================
     const int b = lane & 7, ccs = lane >> 3;               // this lane's footprint items: row block b, cell columns ccs + 4 u
     for (int k = 0, tile = blockIdx.x; tile < tp.n_tiles; ++k, tile += gridDim.x) {
       const int s = k & 1;
-      const int ty = tile / tp.tiles_x, txi = tile - ty * tp.tiles_x;
       const int j0 = txi * kTileCols, jw = min(kTileCols, p.canvas_w - j0), j1 = j0 + jw - 1;
       const int tb0 = ty * kTileBlocks, nbt = min(kTileBlocks, p.n_blocks - tb0);
+      txi += tp.step_x; ty += tp.step_y;
+      if (txi >= tiles_x) { txi -= tiles_x; ++ty; }
       const int c_lo = (int)__ldg(p.col_lut + j0).x, c_hi = (int)__ldg(p.col_lut + j1).x;
-      bool odd = c_hi - c_lo >= kMaxCellCols || c_hi < c_lo || !tp.src_tma_ok || p.force_exact;
+      const uint2 e = __ldg(p.row_blocks + tb0 + min(b, nbt - 1));
+      const int i0 = (int)(e.x & 0x0fffffffu), n = (int)(e.x >> 28), cr = (int)(e.y & 0xffffu);
+      bool odd = c_hi - c_lo >= kMaxCellCols || c_hi < c_lo || !tp.src_tma_ok;
       // every column's cell inside [c_lo, c_hi]?  (always, for the monotone LUT of a sorted mesh)
 #pragma unroll
       for (int q = 0; q < kTileCols / 32; ++q) {
@@ -300,11 +335,10 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
         odd = odd || cc < c_lo || cc > c_hi;
       }
       odd = __any_sync(0xffffffffu, odd);
+      const bool bad_lut = odd && tp.src_tma_ok;              // (conservative) the cell columns are not the range c_lo .. c_hi
       float bx0 = 3e9f, bx1 = -3e9f, by0 = 3e9f, by1 = -3e9f;
       bool all_out = true;
       if (!odd) {
-        const uint2 e = __ldg(p.row_blocks + tb0 + min(b, nbt - 1));
-        const int i0 = (int)(e.x & 0x0fffffffu), n = (int)(e.x >> 28), cr = (int)(e.y & 0xffffu);
         const float ya = (float)(i0 - p.off_y), yb = (float)(i0 + n - 1 - p.off_y);
         const int trips = (c_hi - c_lo + 4) >> 2;            // warp-uniform
 #pragma unroll 2
@@ -349,13 +383,18 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
       const int iy0 = __reduce_min_sync(0xffffffffu, __float2int_rd(by0 - 0.5f));
       const int iy1 = __reduce_max_sync(0xffffffffu, __float2int_rd(by1 + 0.5f));
 
-      TileInfo f;
-      f.pad[0] = f.pad[1] = f.pad[2] = 0;
-      f.x_lo = f.y_lo = 0; f.pitch = p.src_w; f.shift = 0;
-      f.mode = kGlobal;
-      int shape = -1, c0 = 0;
+      // cell-row runs of the tile's blocks (lanes 0 .. nbt-1 hold block b = lane): run index = record slot
+      const int cr_prev = __shfl_up_sync(0xffffffffu, cr, 1);
+      const unsigned starts = __ballot_sync(0xffffffffu, lane < nbt && (lane == 0 || cr != cr_prev));
+      const int slot = __popc(starts & ((2u << b) - 1u)) - 1;
+      const int n_runs = __popc(starts), ncc = c_hi - c_lo + 1;
+      const bool rec_ok = n_runs <= kRecRuns && ncc >= 1 && ncc <= kRecCols && !all_out && !bad_lut;
+      const int run_first = __fns(starts, 0, min(lane, n_runs - 1) + 1);    // lane r: first block of run r
+      const int run_cr = __shfl_sync(0xffffffffu, cr, run_first);
+
+      int mode = kGlobal, x_lo = 0, y_lo = 0, bpitch = p.src_w, shift = 0, shape = -1, c0 = 0;
       if (!odd && all_out) {
-        f.mode = kBlack;
+        mode = kBlack;
       } else if (!odd && ix0 <= ix1 && iy0 <= iy1) {
         // the box starts at a 16-byte aligned byte of the row (TMA: innermost coordinate x element size % 16 == 0)
         const long long need_w = ((long long)ix1 - ix0 + 1) * 3 + 15, need_h = (long long)iy1 - iy0 + 1;
@@ -364,24 +403,33 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
           if (need_w <= box_w(m) && need_h <= box_h(m)) shape = m;
         if (shape >= 0) {
           c0 = ((ix0 * 3) >> 4) << 2;                       // floor to 16 bytes: first uint32 element of the box
-          f.mode = kStagedMode;
-          f.x_lo = ix0; f.y_lo = iy0;
-          f.pitch = shape == 0 ? box_w(0) : shape == 1 ? box_w(1) : box_w(2);
-          f.shift = ix0 * 3 - (c0 << 2);
+          mode = kStagedMode;
+          x_lo = ix0; y_lo = iy0;
+          bpitch = shape == 0 ? box_w(0) : shape == 1 ? box_w(1) : box_w(2);
+          shift = ix0 * 3 - (c0 << 2);
         }
       }
+      const int r_first = __shfl_sync(0xffffffffu, i0, 0);
+      const int r_last = __shfl_sync(0xffffffffu, i0 + n - 1, nbt - 1);
 
       mbar_wait(&sm.empty[s], ((k >> 1) & 1) ^ 1);           // the workers have left this stage
+      TileInfo &f = sm.info[s];
+      if (lane < kTileBlocks) { f.blk[lane] = e; f.slot[lane] = slot; }
       if (lane == 0) {
-        sm.info[s] = f;
-        if (shape >= 0) {
-          mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(f.pitch * (shape == 0 ? box_h(0) : shape == 1 ? box_h(1) : box_h(2))));
-          tma_load_2d(sm.st[s].box, &tp.maps[shape], c0, iy0, &sm.full[s]);
-        } else {
-          mbar_arrive(&sm.full[s]);
-        }
+        f.x_lo = x_lo; f.y_lo = y_lo; f.pitch = bpitch; f.shift = shift; f.mode = mode;
+        f.r_first = r_first; f.n_rows = r_last - r_first + 1; f.c_lo = c_lo; f.rec_ok = rec_ok ? 1 : 0;
       }
       __syncwarp();
+      const uint32_t box_bytes = shape < 0 ? 0u : (uint32_t)(bpitch * (shape == 0 ? box_h(0) : shape == 1 ? box_h(1) : box_h(2)));
+      const uint32_t rec_bytes = rec_ok ? (uint32_t)(ncc * kHinvRow * 4) : 0u;
+      if (lane == 0) {
+        if (box_bytes + rec_bytes) mbar_arrive_expect_tx(&sm.full[s], box_bytes + rec_bytes * n_runs);
+        else mbar_arrive(&sm.full[s]);
+        if (shape >= 0) tma_load_2d(sm.st[s].box, &tp.maps[shape], c0, iy0, &sm.full[s]);
+      }
+      __syncwarp();
+      if (rec_ok && lane < n_runs)                           // one bulk copy per cell row: the records of cells c_lo .. c_hi
+        bulk_g2s(&sm.st[s].rec[lane][0][0], p.cell_fast + (size_t)(run_cr * p.grid_cols + c_lo) * 3, rec_bytes, &sm.full[s]);
     }
     return;
   }
@@ -390,38 +438,37 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
   const int lane_col = (warp & 3) * 32 + lane;
   const int half = warp >> 2;
   const uint32_t pitch = (uint32_t)p.canvas_w * 3u;
+  uint2 cl_next = __ldg(p.col_lut + min(txi * kTileCols + lane_col, p.canvas_w - 1));
   for (int k = 0, tile = blockIdx.x; tile < tp.n_tiles; ++k, tile += gridDim.x) {
     const int s = k & 1;
-    const int ty = tile / tp.tiles_x, txi = tile - ty * tp.tiles_x;
     const int j0 = txi * kTileCols, jw = min(kTileCols, p.canvas_w - j0);
-    const int tb0 = ty * kTileBlocks, nbt = min(kTileBlocks, p.n_blocks - tb0);
+    const int nbt = min(kTileBlocks, p.n_blocks - ty * kTileBlocks);
+    txi += tp.step_x; ty += tp.step_y;
+    if (txi >= tiles_x) { txi -= tiles_x; ++ty; }
     const int j = j0 + lane_col;
     const bool col_ok = j < p.canvas_w;
-    const uint2 cl = __ldg(p.col_lut + (col_ok ? j : p.canvas_w - 1));
+    const uint2 cl = cl_next;
     const int x = j - p.off_x;
-    const uint2 e_first = __ldg(p.row_blocks + tb0), e_last = __ldg(p.row_blocks + tb0 + nbt - 1);
-    const int r_first = (int)(e_first.x & 0x0fffffffu);
-    const int r_last = (int)(e_last.x & 0x0fffffffu) + (int)(e_last.x >> 28) - 1;
-    const int n_rows = r_last - r_first + 1;
-    const int tb = tb0 + half * kWarpBlocks;
     const int nb = max(0, min(kWarpBlocks, nbt - half * kWarpBlocks));
     uint8_t *out_tile = sm.out[s];
 
     if (tp.store_mode == 2) bulk_wait_read_but_one();        // this thread's row store of two tiles ago has read out[s]
-    mbar_wait(&sm.full[s], (k >> 1) & 1);                    // box + info of this tile have landed
-    const TileInfo f = sm.info[s];
-    const uint8_t *box = sm.st[s].box;
-    if (f.mode == kStagedMode) {
-      tile_warp_work<true, kBlend>(p, f, box, out_tile, cl, x, col_ok, lane_col, tb, nb, r_first);
-    } else if (f.mode == kGlobal) {
-      tile_warp_work<false, kBlend>(p, f, box, out_tile, cl, x, col_ok, lane_col, tb, nb, r_first);
+    mbar_wait(&sm.full[s], (k >> 1) & 1);                    // box, records and info of this tile have landed
+    if (tile + (int)gridDim.x < tp.n_tiles)                  // the next tile's column entry: in flight during this tile
+      cl_next = __ldg(p.col_lut + min(txi * kTileCols + lane_col, p.canvas_w - 1));
+    const TileInfo &f = sm.info[s];
+    const int mode = f.mode, r_first = f.r_first, n_rows = f.n_rows;
+    if (mode == kStagedMode) {
+      tile_warp_work<true, kBlend>(p, f, sm.st[s], out_tile, cl, x, col_ok, lane_col, half * kWarpBlocks, nb);
+    } else if (mode == kGlobal) {
+      tile_warp_work<false, kBlend>(p, f, sm.st[s], out_tile, cl, x, col_ok, lane_col, half * kWarpBlocks, nb);
     } else {                                                  // kBlack: clear (or fill with the centre image) the tile
       if (!kBlend) {
         for (int q = tid; q < n_rows * (kOutPitch / 16); q += kWorkerThreads)
           reinterpret_cast<uint4 *>(out_tile)[q] = make_uint4(0u, 0u, 0u, 0u);
       } else {
         for (int bi = 0; bi < nb; ++bi) {
-          const uint2 e = __ldg(p.row_blocks + tb + bi);
+          const uint2 e = f.blk[half * kWarpBlocks + bi];
           const int i0 = (int)(e.x & 0x0fffffffu), n = (int)(e.x >> 28);
           for (int r = 0; r < n; ++r) {
             const uint32_t val = centre_px(p, x, i0 + r - p.off_y, col_ok);
@@ -525,6 +572,8 @@ int launch_warp_tile(const WarpParams &w, const int *col_ext, bool words, cudaSt
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int grid = min(tp.n_tiles, sm_count_cached() * APAP_TILE_CTAS);
+  tp.step_x = grid % tp.tiles_x;
+  tp.step_y = grid / tp.tiles_x;
   if (w.centre) k_warp_tile<true><<<grid, kTileThreads, smem, st>>>(tp);
   else k_warp_tile<false><<<grid, kTileThreads, smem, st>>>(tp);
   return check_cuda(cudaGetLastError(), "k_warp_tile launch");

@@ -117,6 +117,9 @@ class SymmetricPanorama:
         band = self.local[px_row0:px_row1]
         if band.numel() == 0:
             return
+        if self.world != 2 and not self.supported:
+            raise rt.ApapError("broadcast_band: this group has no NVLS multicast mapping (multicast_ptr == 0) or "
+                               "canvas_w % 16 != 0 -- assemble the panorama with gather_bands instead")
         if self.world == 2:
             # two GPUs: one unicast peer copy beats the multicast store rate (measured 129 us against 190 us for
             # the 62 MB band of c3); from three GPUs on a rank would send its band N - 1 times and multicast wins
@@ -131,6 +134,15 @@ class SymmetricPanorama:
     def barrier(self):
         """Every rank's band has landed everywhere once all ranks are past this (device-side, on the current stream)."""
         self.handle.barrier()
+
+
+def _image_on_device(rt, torch, device, img):
+    """uint8, contiguous, on ``device`` -- what ``APAP._warp`` does with its image argument."""
+    if isinstance(img, np.ndarray):
+        return rt.to_device(torch, device, img.astype(np.uint8, copy=False))
+    if img.dtype != torch.uint8:
+        raise TypeError("a device image must be a uint8 tensor")
+    return img.contiguous()
 
 
 class ShardedAPAP:
@@ -169,7 +181,7 @@ class ShardedAPAP:
         full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
         full[...] = np.eye(3, dtype=np.float32)
         full[s.cell_row0:s.cell_row1] = local_h_rows
-        src_dev = ori_img if not isinstance(ori_img, np.ndarray) else rt.to_device(torch, device, ori_img)
+        src_dev = _image_on_device(rt, torch, device, ori_img)
         tables = st.warp_tables_device(full, self.col_cell, self.row_cell, int(ori_img.shape[1]),
                                        int(ori_img.shape[0]), device, s.px_row0, s.px_row1)
         return st.warp_device(src_dev, tables, self.grid_cols)
@@ -180,17 +192,24 @@ class ShardedAPAP:
     def local_warp_panorama(self, ori_img, local_h_rows, pano: "SymmetricPanorama", fused_stores: bool = False):
         """``local_warp_band`` + ``panorama`` without an all-gather: the owned canvas rows are warped into this rank's
         panorama and broadcast into every other GPU's through the NVLS multicast mapping (``fused_stores``: by the
-        warp kernel's own stores instead of a broadcast kernel -- one kernel, but its 96-byte row fragments use the
-        links 2.5x worse); returns this rank's (complete) panorama tensor."""
+        warp kernel's own stores -- whole 384-byte tile rows out of shared memory -- instead of a broadcast kernel);
+        a group barrier on entry (peers may still read the previous pass) and on exit; returns this rank's
+        (complete) panorama tensor.  Raises ``ApapError`` when the group has no multicast mapping."""
         from . import _runtime as rt
 
         st, s = self.stitcher, self.me
+        if (fused_stores or pano.world != 2) and not pano.supported:
+            # a bare offset would pass for a multicast address and multimem.st would fault the GPU
+            raise rt.ApapError("local_warp_panorama: this group has no NVLS multicast mapping (multicast_ptr == 0) or "
+                               "canvas_w % 16 != 0 -- use local_warp_band + panorama (all-gather) instead")
         torch, device = rt.torch_cuda(st.device)
+        # no rank may store into a peer's panorama while that peer still reads the previous pass
+        pano.barrier()
         st.invert_grid(local_h_rows, device)
         full = np.zeros((self.grid_rows, self.grid_cols, 3, 3), dtype=np.float32)
         full[...] = np.eye(3, dtype=np.float32)
         full[s.cell_row0:s.cell_row1] = local_h_rows
-        src_dev = ori_img if not isinstance(ori_img, np.ndarray) else rt.to_device(torch, device, ori_img)
+        src_dev = _image_on_device(rt, torch, device, ori_img)
         tables = st.warp_tables_device(full, self.col_cell, self.row_cell, int(ori_img.shape[1]),
                                        int(ori_img.shape[0]), device, s.px_row0, s.px_row1)
         if fused_stores:

@@ -538,3 +538,41 @@ def test_certified_inverse_never_certifies_a_different_rounding(family):
     assert np.array_equal(f[keep].view(np.uint32), want.view(np.uint32))
     if family in ("uniform", "row_scales", "col_scales", "hilbert"):
         assert flag.mean() < 0.01
+
+
+def test_compat_modules_have_the_reference_module_names_and_signatures():
+    """the reference's driver does ``from apap_utils import *`` and defines ``class APAP`` in module
+    ``apap`` (pyviz/apap.py:15,21).  With ``compat/`` on sys.path the same imports resolve to this package, with the
+    reference's parameter names (pyviz/apap.py:22,35,63,92,103,121,172,186; pyviz/apap_utils.py:10,23,40,75)."""
+    import importlib
+    import inspect
+    compat = os.path.join(REPO, "compat")
+    sys.path.insert(0, compat)
+    try:
+        for name in ("apap", "apap_utils"):
+            sys.modules.pop(name, None)
+        apap_mod = importlib.import_module("apap")
+        utils_mod = importlib.import_module("apap_utils")
+    finally:
+        sys.path.remove(compat)
+    assert sorted(utils_mod.__all__) == ["final_size", "get_mesh", "get_vertice", "uniform_blend"]
+    for fn in utils_mod.__all__:                                   # star-imported into `apap`, like the reference
+        assert getattr(apap_mod, fn) is getattr(utils_mod, fn)
+    params = lambda f: list(inspect.signature(f).parameters)       # noqa: E731
+    assert params(utils_mod.get_mesh) == ["size", "mesh_size", "start"]
+    assert params(utils_mod.get_vertice) == ["size", "mesh_size", "offsets"]
+    assert params(utils_mod.final_size) == ["src_img", "dst_img", "project_H"]
+    assert params(utils_mod.uniform_blend) == ["img1", "img2"]
+    cls = apap_mod.APAP
+    assert params(cls.__init__)[:5] == ["self", "gamma", "sigma", "final_size", "offset"]
+    assert params(cls.getNormalize2DPts) == ["point"] and params(cls.getConditionerFromPts) == ["point"]
+    assert params(cls.point_normalize) == ["nf", "c"] and params(cls.matrix_generate) == ["sample_n", "cf1", "cf2"]
+    assert params(cls.local_homography) == ["self", "src_point", "dst_point", "vertices"]
+    assert params(cls.warp_coordinate_estimate) == ["pt", "homography"]
+    assert params(cls.local_warp) == ["self", "ori_img", "local_homography", "mesh", "progress"]
+    st = cls(0.5, 100, [64, 48], [3, 2])
+    assert (st.gamma, st.sigma, st.final_width, st.final_height, st.offset_x, st.offset_y) == (0.5, 100, 64, 48, 3, 2)
+    mesh = utils_mod.get_mesh((64, 48), 5)
+    assert mesh.shape == (2, 5) and mesh.dtype == np.float64
+    for name in ("apap", "apap_utils"):
+        sys.modules.pop(name, None)
