@@ -19,7 +19,7 @@ KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
 WARP_BLOCK_ROWS = 4
-ABI_VERSION = 14
+ABI_VERSION = 15
 KP_BLOCK = 8
 KP_BLOCK_FLOATS = 528
 GRAM_TCGEN05 = 0
@@ -42,7 +42,8 @@ SIGNATURES = {
     "apap_local_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
-                          c_void_p]),
+                          c_void_p, c_size_t, c_void_p]),
+    "apap_warp_scratch_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "apap_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "apap_pipe_probe": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
     "apap_warp_perspective": (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_void_p, c_int, c_int, c_void_p, c_int,

@@ -806,6 +806,7 @@ class APAP:
         if multicast_ptr is None and out is None:
             out = torch.empty((tables.row1 - tables.row0, fw, 3), dtype=torch.uint8, device=device)
         ch, cw = (centre_dev.shape[0], centre_dev.shape[1]) if centre_dev is not None else (0, 0)
+        scratch = self._warp_scratch(torch, device, lib, fw, tables.n_blocks)
         with torch.cuda.device(device):
             rt.check(lib.apap_warp(
                 src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
@@ -815,8 +816,22 @@ class APAP:
                 int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
                 n_bytes if multicast_ptr is not None else out.numel(),
                 (rt.WARP_FORCE_EXACT if force_exact else 0) | (rt.WARP_LEGACY if legacy else 0),
-                1 if multicast_ptr is not None else 0, rt.stream_ptr(torch, device)), "apap_warp")
+                1 if multicast_ptr is not None else 0, scratch.data_ptr(), scratch.numel(),
+                rt.stream_ptr(torch, device)), "apap_warp")
         return out
+
+    def _warp_scratch(self, torch, device, lib, canvas_w, n_blocks):
+        """The tile engine's per-tile records (``apap_warp_scratch_bytes``): one device buffer per instance, grown on
+        demand and reused by every call (calls on one stream are ordered, so reuse is safe)."""
+        import ctypes
+        need = ctypes.c_size_t()
+        rt.check(lib.apap_warp_scratch_bytes(int(canvas_w), int(n_blocks), ctypes.byref(need)), "apap_warp_scratch_bytes")
+        hit = getattr(self, "_scratch", None)
+        extra = 0
+        if hit is None or hit.device != device or hit.numel() < max(need.value, 16) + extra:
+            hit = torch.zeros(max(need.value, 16) + extra, dtype=torch.uint8, device=device)
+            self._scratch = hit
+        return hit
 
     def invert_grid(self, local_homography, device=None) -> int:
         """The per-cell ``np.linalg.inv`` of ``local_warp`` (pyviz/apap.py:201-203), stored back into the caller's

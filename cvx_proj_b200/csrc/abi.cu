@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "warp_common.cuh"
 
 namespace apap {
 
@@ -111,7 +112,8 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
               const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks, int grid_cols,
               int canvas_w, int off_x, int off_y, int row0, int row1, const uint8_t *centre, int centre_h,
-              int centre_w, uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *stream) {
+              int centre_w, uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *scratch,
+              size_t scratch_bytes, void *stream) {
   if (!src || !cell_fast || !cell_hinv || !col_lut || !out_band) return fail(APAP_E_BADARG, "null pointer");
   if (!col_extent && !(flags & APAP_WARP_LEGACY)) return fail(APAP_E_BADARG, "warp: null col_extent");
   if (flags & ~(APAP_WARP_FORCE_EXACT | APAP_WARP_LEGACY)) return fail(APAP_E_BADARG, "warp: unknown flag");
@@ -122,8 +124,14 @@ int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, 
   if (out_band_bytes < (size_t)(row1 - row0) * (size_t)canvas_w * 3)
     return fail(APAP_E_BADARG, "warp: out_band is smaller than the rows [row0, row1) of the canvas");
   return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, col_extent, row_blocks, n_blocks, grid_cols,
-                     canvas_w, off_x, off_y, row0, centre, centre_h, centre_w, out_band, out_band_bytes, flags,
-                     multicast, static_cast<cudaStream_t>(stream));
+                     canvas_w, off_x, off_y, row0, row1, centre, centre_h, centre_w, out_band, out_band_bytes, flags,
+                     multicast, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int apap_warp_scratch_bytes(int canvas_w, int n_blocks, size_t *bytes) {
+  if (!bytes || canvas_w <= 0 || n_blocks < 0) return fail(APAP_E_BADARG, "warp_scratch_bytes: bad arguments");
+  *bytes = warp_tile_scratch_bytes(canvas_w, n_blocks);
+  return 0;
 }
 
 int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream) {

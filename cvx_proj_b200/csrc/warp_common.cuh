@@ -19,6 +19,7 @@ struct WarpParams {
   const uint8_t *centre;
   uint8_t *out;                // first byte of canvas row `row0`
   int row0;                    // first canvas row of the band `out` holds
+  int band_rows;               // canvas rows `out` holds
   int n_blocks;
   int chunks_per_row;          // ceil(canvas_w / 32)
   int src_h, src_w;
@@ -79,6 +80,7 @@ __device__ __forceinline__ void enter_cell_row(const WarpParams &p, const uint2 
   }
 }
 
-int launch_warp_tile(const WarpParams &w, const int *col_ext, bool words, cudaStream_t st);
+int launch_warp_tile(const WarpParams &w, const int *col_ext, bool words, void *scratch, size_t scratch_bytes, cudaStream_t st);
+size_t warp_tile_scratch_bytes(int canvas_w, int n_blocks);
 
 }  // namespace apap

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 14
+#define APAP_ABI_VERSION 15
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -154,6 +154,7 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
  *               memory, shuffle re-pack) instead of the tile engine (csrc/warp_tile.cu: the source footprint of
  *               a 128 x 32 canvas tile staged in shared memory with TMA bulk copies, LDS gathers, the output
  *               tile assembled in shared memory and stored as whole row segments).  Same bytes either way.
+ *   scratch   : device scratch of at least apap_warp_scratch_bytes(canvas_w, n_blocks) bytes (see below)
  *   multicast   : non-zero = out_band is an NVLS multicast address (one mapping of the same panorama buffer on every
  *                 GPU of the group, e.g. torch symmetric memory's multicast_ptr + band offset): the kernel stores with
  *                 multimem.st, so the NVSwitch writes this rank's row band into every GPU's panorama -- the panorama
@@ -167,7 +168,15 @@ int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, 
               const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks,
               int grid_cols, int canvas_w, int off_x, int off_y, int row0, int row1,
               const uint8_t *centre, int centre_h, int centre_w,
-              uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *stream);
+              uint8_t *out_band, size_t out_band_bytes, int flags, int multicast,
+              void *scratch, size_t scratch_bytes, void *stream);
+/*
+ * Device scratch apap_warp needs for a band of n_blocks row blocks on a canvas_w wide canvas (the tile engine's
+ * per-tile records: which source box a 128 x 32 canvas tile gathers from, its rows by cell row; 192 bytes per
+ * tile, written by a preparation kernel at the start of every call).  16-byte aligned, caller-owned, may be reused
+ * by the next call on the same stream; APAP_WARP_LEGACY does not touch it (NULL / 0 allowed).
+ */
+int apap_warp_scratch_bytes(int canvas_w, int n_blocks, size_t *bytes);
 
 /*
  * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,

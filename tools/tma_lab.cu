@@ -37,6 +37,33 @@ __global__ void k(const __grid_constant__ Params p, const __grid_constant__ CUte
   atomicAdd(p.out, sum);
 }
 
+// latency of one box load on an otherwise idle SM / GPU: globaltimer around issue -> barrier flip, `reps` times
+__global__ void k_lat(const __grid_constant__ CUtensorMap m, int bytes, int c0, int c1, int reps, long long *out) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 32768);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    long long best = 1 << 30, sum = 0;
+    for (int r = 0; r < reps; ++r) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(sm)),
+                   "l"(reinterpret_cast<uint64_t>(&m)), "r"(c0 + 128 * ((r * 7 + blockIdx.x) % 5)), "r"(c1 + 41 * ((r + blockIdx.x) % 13)), "r"(s32(bar))
+                   : "memory");
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(s32(bar)), "r"(r & 1) : "memory");
+      }
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      const long long d = (long long)(t1 - t0);
+      best = d < best ? d : best; sum += d;
+    }
+    out[2 * blockIdx.x] = best; out[2 * blockIdx.x + 1] = sum / reps;
+  }
+}
+
 typedef CUresult (*Enc)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -60,6 +87,31 @@ int main(int argc, char **argv) {
       {"u8 box 256x40 c0=48", CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 40, 48, 40},
       {"u8 box 256x40 c0=33", CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 40, 33, 40},
   };
+  if (argc > 1 && atoi(argv[1]) == 99) {                     // latency of box loads, alone and with every SM loading
+    const int W2 = 7680, H2 = 4320, pitch2 = W2 * 3;
+    uint8_t *d2; cudaMalloc(&d2, (size_t)pitch2 * H2); cudaMemset(d2, 7, (size_t)pitch2 * H2);
+    long long *lo; cudaMalloc(&lo, 8 * 2 * 1024);
+    struct { int bw, bh; } shapes[] = {{128, 40}, {64, 40}, {32, 40}, {128, 10}, {128, 1}};
+    for (auto &sh : shapes)
+      for (int grid : {1, 148, 444}) {
+        const cuuint64_t dims[2] = {(cuuint64_t)(pitch2 / 4), (cuuint64_t)H2};
+        const cuuint64_t strides[1] = {(cuuint64_t)pitch2};
+        const cuuint32_t box[2] = {(cuuint32_t)sh.bw, (cuuint32_t)sh.bh};
+        const cuuint32_t ones[2] = {1, 1};
+        CUtensorMap m;
+        enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d2, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cudaFuncSetAttribute(k_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+        k_lat<<<grid, 32, 40000>>>(m, sh.bw * 4 * sh.bh, 256, 100, 64, lo);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        long long h[2 * 444]; cudaMemcpy(h, lo, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
+        long long mb = 1 << 30, ma = 0;
+        for (int i = 0; i < grid; ++i) { mb = h[2 * i] < mb ? h[2 * i] : mb; ma += h[2 * i + 1]; }
+        printf("box %4d B x %2d rows (%5d B) grid %3d: %s best %lld ns mean %lld ns\n", sh.bw * 4, sh.bh, sh.bw * 4 * sh.bh, grid,
+               cudaGetErrorName(e2), mb, ma / grid);
+      }
+    return 0;
+  }
   for (int variant = 0; variant < 2; ++variant)
     for (int ci = 0; ci < (int)(sizeof(cfgs) / sizeof(cfgs[0])); ++ci) {
       if ((only >= 0 && ci != only) || (only_variant >= 0 && variant != only_variant)) continue;
