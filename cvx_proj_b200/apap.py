@@ -429,12 +429,15 @@ class _PinnedStage:
 
 class WarpTables(NamedTuple):
     """Device-resident inputs of ``apap_warp`` for one inverted grid and one band of canvas rows
-    (see ``build_warp_tables`` / ``build_row_blocks``)."""
+    (see ``build_warp_tables`` / ``build_row_blocks``): cell records, LUTs, row blocks and -- when the source rows
+    are 16-byte aligned -- the tile engine's per-tile records.  They depend on the grid and the geometry, not on the
+    images: build once, warp any number of images."""
     cell_fast: object       # float32 [cells * 12]
     cell_hinv: object       # float32 [cells * 9]
     col_lut: object         # int32 [canvas_w * 2]
     col_extent: object      # int32 [grid_cols * 2]
     row_blocks: object      # int32 [n_blocks * 2]
+    tiles: object           # uint8: the tile engine's records (``apap_warp_tiles``), None = strip kernel only
     n_blocks: int
     row0: int               # the band of canvas rows the blocks cover
     row1: int
@@ -788,8 +791,21 @@ class APAP:
             rt.check(lib.apap_warp_tables(hinv_dev.data_ptr(), views[3].data_ptr(), views[4].data_ptr(), gr, gc,
                                           int(self.offset_x), int(self.offset_y), int(src_w), int(src_h),
                                           fast.data_ptr(), rt.stream_ptr(torch, device)), "apap_warp_tables")
+        tiles = None
+        if (int(src_w) * 3) % 16 == 0 and blocks.shape[0]:         # tile engine: 16-byte aligned source rows
+            import ctypes
+            need = ctypes.c_size_t()
+            rt.check(lib.apap_warp_tiles_bytes(int(self.final_width), int(blocks.shape[0]), ctypes.byref(need)),
+                     "apap_warp_tiles_bytes")
+            tiles = torch.empty(max(int(need.value), 16), dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                rt.check(lib.apap_warp_tiles(fast.data_ptr(), hinv_dev.data_ptr(), views[1].data_ptr(), views[3].data_ptr(),
+                                             views[2].data_ptr(), int(blocks.shape[0]), gc, int(self.final_width),
+                                             int(self.offset_x), int(self.offset_y), int(src_h), int(src_w),
+                                             tiles.data_ptr(), tiles.numel(), rt.stream_ptr(torch, device)),
+                         "apap_warp_tiles")
         return WarpTables(fast, hinv_dev, views[1].view(torch.int32), views[3].view(torch.int32),
-                          views[2].view(torch.int32), int(blocks.shape[0]), int(row0), int(row1))
+                          views[2].view(torch.int32), tiles, int(blocks.shape[0]), int(row0), int(row1))
 
     def warp_device(self, src_dev, tables, grid_cols, centre_dev=None, out=None, force_exact=False, multicast_ptr=None,
                     legacy=False):
@@ -806,32 +822,19 @@ class APAP:
         if multicast_ptr is None and out is None:
             out = torch.empty((tables.row1 - tables.row0, fw, 3), dtype=torch.uint8, device=device)
         ch, cw = (centre_dev.shape[0], centre_dev.shape[1]) if centre_dev is not None else (0, 0)
-        scratch = self._warp_scratch(torch, device, lib, fw, tables.n_blocks)
         with torch.cuda.device(device):
             rt.check(lib.apap_warp(
                 src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_fast.data_ptr(),
-                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(), tables.col_extent.data_ptr(),
+                tables.cell_hinv.data_ptr(), tables.col_lut.data_ptr(),
                 tables.row_blocks.data_ptr(), tables.n_blocks, grid_cols, fw, int(self.offset_x), int(self.offset_y),
                 tables.row0, tables.row1, centre_dev.data_ptr() if centre_dev is not None else None, ch, cw,
                 int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
                 n_bytes if multicast_ptr is not None else out.numel(),
                 (rt.WARP_FORCE_EXACT if force_exact else 0) | (rt.WARP_LEGACY if legacy else 0),
-                1 if multicast_ptr is not None else 0, scratch.data_ptr(), scratch.numel(),
+                1 if multicast_ptr is not None else 0,
+                tables.tiles.data_ptr() if tables.tiles is not None else None,
                 rt.stream_ptr(torch, device)), "apap_warp")
         return out
-
-    def _warp_scratch(self, torch, device, lib, canvas_w, n_blocks):
-        """The tile engine's per-tile records (``apap_warp_scratch_bytes``): one device buffer per instance, grown on
-        demand and reused by every call (calls on one stream are ordered, so reuse is safe)."""
-        import ctypes
-        need = ctypes.c_size_t()
-        rt.check(lib.apap_warp_scratch_bytes(int(canvas_w), int(n_blocks), ctypes.byref(need)), "apap_warp_scratch_bytes")
-        hit = getattr(self, "_scratch", None)
-        extra = 0
-        if hit is None or hit.device != device or hit.numel() < max(need.value, 16) + extra:
-            hit = torch.zeros(max(need.value, 16) + extra, dtype=torch.uint8, device=device)
-            self._scratch = hit
-        return hit
 
     def invert_grid(self, local_homography, device=None) -> int:
         """The per-cell ``np.linalg.inv`` of ``local_warp`` (pyviz/apap.py:201-203), stored back into the caller's

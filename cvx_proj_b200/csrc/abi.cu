@@ -110,12 +110,10 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 }
 
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-              const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks, int grid_cols,
-              int canvas_w, int off_x, int off_y, int row0, int row1, const uint8_t *centre, int centre_h,
-              int centre_w, uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *scratch,
-              size_t scratch_bytes, void *stream) {
+              const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x,
+              int off_y, int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
+              size_t out_band_bytes, int flags, int multicast, const void *tiles, void *stream) {
   if (!src || !cell_fast || !cell_hinv || !col_lut || !out_band) return fail(APAP_E_BADARG, "null pointer");
-  if (!col_extent && !(flags & APAP_WARP_LEGACY)) return fail(APAP_E_BADARG, "warp: null col_extent");
   if (flags & ~(APAP_WARP_FORCE_EXACT | APAP_WARP_LEGACY)) return fail(APAP_E_BADARG, "warp: unknown flag");
   if (n_blocks < 0 || (n_blocks > 0 && !row_blocks)) return fail(APAP_E_BADARG, "warp: bad row blocks");
   if (src_h <= 0 || src_w <= 0 || canvas_w <= 0 || grid_cols <= 0) return fail(APAP_E_BADARG, "warp: sizes must be > 0");
@@ -123,15 +121,33 @@ int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, 
   if (row0 < 0 || row1 < row0) return fail(APAP_E_BADARG, "warp: bad row band");
   if (out_band_bytes < (size_t)(row1 - row0) * (size_t)canvas_w * 3)
     return fail(APAP_E_BADARG, "warp: out_band is smaller than the rows [row0, row1) of the canvas");
-  return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, col_extent, row_blocks, n_blocks, grid_cols,
-                     canvas_w, off_x, off_y, row0, row1, centre, centre_h, centre_w, out_band, out_band_bytes, flags,
-                     multicast, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+  return launch_warp(src, src_h, src_w, cell_fast, cell_hinv, col_lut, row_blocks, n_blocks, grid_cols, canvas_w, off_x,
+                     off_y, row0, row1, centre, centre_h, centre_w, out_band, out_band_bytes, flags, multicast, tiles,
+                     static_cast<cudaStream_t>(stream));
 }
 
-int apap_warp_scratch_bytes(int canvas_w, int n_blocks, size_t *bytes) {
-  if (!bytes || canvas_w <= 0 || n_blocks < 0) return fail(APAP_E_BADARG, "warp_scratch_bytes: bad arguments");
-  *bytes = warp_tile_scratch_bytes(canvas_w, n_blocks);
+int apap_warp_tiles_bytes(int canvas_w, int n_blocks, size_t *bytes) {
+  if (!bytes || canvas_w <= 0 || n_blocks < 0) return fail(APAP_E_BADARG, "warp_tiles_bytes: bad arguments");
+  *bytes = warp_tiles_bytes(canvas_w, n_blocks);
   return 0;
+}
+
+int apap_warp_tiles(const float *cell_fast, const float *cell_hinv, const uint32_t *col_lut, const int *col_extent,
+                    const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x, int off_y, int src_h,
+                    int src_w, void *tiles, size_t tiles_bytes, void *stream) {
+  if (!cell_fast || !cell_hinv || !col_lut || !col_extent || (n_blocks > 0 && !row_blocks))
+    return fail(APAP_E_BADARG, "warp_tiles: null pointer");
+  if (n_blocks < 0 || grid_cols <= 0 || canvas_w <= 0 || src_h <= 0 || src_w <= 0) return fail(APAP_E_BADARG, "warp_tiles: bad sizes");
+  if ((reinterpret_cast<uintptr_t>(cell_fast) & 15u) || (reinterpret_cast<uintptr_t>(col_lut) & 7u) ||
+      (reinterpret_cast<uintptr_t>(row_blocks) & 7u) || (reinterpret_cast<uintptr_t>(col_extent) & 7u))
+    return fail(APAP_E_ALIGN, "warp_tiles: cell_fast must be 16-byte, col_lut / row_blocks / col_extent 8-byte aligned");
+  WarpParams p;
+  memset(&p, 0, sizeof(p));
+  p.cell_fast = reinterpret_cast<const float4 *>(cell_fast); p.cell_hinv = cell_hinv;
+  p.col_lut = reinterpret_cast<const uint2 *>(col_lut); p.row_blocks = reinterpret_cast<const uint2 *>(row_blocks);
+  p.n_blocks = n_blocks; p.grid_cols = grid_cols; p.canvas_w = canvas_w; p.off_x = off_x; p.off_y = off_y;
+  p.src_h = src_h; p.src_w = src_w;
+  return launch_warp_tiles(p, col_extent, tiles, tiles_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, void *stream) {

@@ -53,10 +53,9 @@ int launch_eig(const float *partials, const double *tmats, int batch, int cells,
 int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
                   double gamma, double *out, cudaStream_t st);
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-                const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks, int grid_cols,
-                int canvas_w, int off_x, int off_y, int row0, int row1, const uint8_t *centre, int centre_h, int centre_w,
-                uint8_t *out_band, size_t out_band_bytes, int flags, int multicast, void *scratch, size_t scratch_bytes,
-                cudaStream_t st);
+                const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x,
+                int off_y, int row0, int row1, const uint8_t *centre, int centre_h, int centre_w, uint8_t *out_band,
+                size_t out_band_bytes, int flags, int multicast, const void *tiles, cudaStream_t st);
 int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, cudaStream_t st);
 int launch_probe(int kind, int iters, float *sink, double *ops, cudaStream_t st);
 int launch_multicast_copy(const void *src, void *mc_dst, size_t bytes, cudaStream_t st);

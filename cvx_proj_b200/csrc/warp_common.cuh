@@ -80,7 +80,9 @@ __device__ __forceinline__ void enter_cell_row(const WarpParams &p, const uint2 
   }
 }
 
-int launch_warp_tile(const WarpParams &w, const int *col_ext, bool words, void *scratch, size_t scratch_bytes, cudaStream_t st);
-size_t warp_tile_scratch_bytes(int canvas_w, int n_blocks);
+int launch_warp_tile(const WarpParams &w, bool words, const void *tiles, cudaStream_t st);
+int launch_warp_tiles(const WarpParams &w, const int *col_ext, void *tiles, size_t tiles_bytes, cudaStream_t st);
+bool warp_tile_usable(const WarpParams &w);
+size_t warp_tiles_bytes(int canvas_w, int n_blocks);
 
 }  // namespace apap

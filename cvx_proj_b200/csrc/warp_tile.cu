@@ -1,10 +1,11 @@
 // K3, tile engine -- mesh warp through shared-memory tiles (reference APAP.local_warp pixel loop,
 // pyviz/apap.py:206-215), optionally fused with K4 (pyviz/apap_utils.py:75-88, pyviz/apap.py:259-261).
 //
-// Two kernels per apap_warp call.  A tile is 128 canvas columns x 8 consecutive row blocks (<= 32 rows).
+// A tile is 128 canvas columns x 8 consecutive row blocks (<= 32 rows).
 //
-// k_tile_prep, one warp per tile: everything about a tile that does not depend on the images, written as one
-//   192-byte TileInfo record into caller-provided scratch --
+// k_tile_prep (apap_warp_tiles: part of the warp tables, built once per inverted grid and row band like the
+//   cell records), one warp per tile: everything about a tile that does not depend on the images, written as
+//   one 192-byte TileInfo record --
 //     footprint: lane = (cell column, row block) maps the four corners of that pixel rectangle of the
 //     tile through the cell's H^-1 (float32 is enough: the result is widened by half a pixel).  Inside a
 //     fast-path cell the maps are ratios of affine functions with a denominator of constant sign, so
@@ -13,10 +14,10 @@
 //     the tile's rows grouped by cell row ("runs"); the mode:
 //       black   every cell of the tile maps outside the source: the workers only clear their output
 //       staged  gather from the staged box
-//       global  no box (it fits none of the shapes, source rows not 16-byte aligned, column LUT not
-//               monotone, forced float64): same arithmetic with a bounds test, gathers from global memory
+//       global  no box (it fits none of the shapes, column LUT not monotone): same arithmetic with a
+//               bounds test, gathers from global memory
 //
-// k_warp_tile, persistent warp-specialised CTAs (8 worker warps + 1 producer warp) that claim tiles dynamically
+// k_warp_tile (apap_warp), persistent warp-specialised CTAs (8 worker warps + 1 producer warp) that claim tiles dynamically
 //   (one global counter per launch):
 //   producer warp, one tile ahead of the workers (two-stage ring, full / empty mbarriers): streams the
 //     tile records into the stage and issues ONE 2-D tensor-map TMA copy (cp.async.bulk.tensor.2d, SASS UTMALDG)
@@ -130,12 +131,11 @@ struct TileParams {
   CUtensorMap out_map;           // the output band as uint32 [band_rows][canvas_w * 3 / 4], box = 16 rows x 96 bytes
   WarpParams w;
   const int2 *col_ext;           // [grid_cols] {first, last} canvas column of the cell column
-  int src_tma_ok;                // source rows 16-byte aligned and the maps encoded: boxes can be staged
   int store_mode;                // 0 bytes, 1 words, 2 TMA (one tensor-map store per warp block), 3 multimem
   int tiles_x, n_tiles;
   int slot;                      // which pair of tile counters this launch uses
   int lab;                       // timing experiments only (APAP_TILE_LAB): 1 workers skip the pixel work, 2 no L2 prefetch
-  TileInfo *tiles;               // [n_tiles] scratch: written by k_tile_prep, streamed by the producer warps
+  TileInfo *tiles;               // [n_tiles]: written by k_tile_prep (apap_warp_tiles), streamed by the producer warps
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(256) k_tile_prep(const __grid_constant__ TileP
 #pragma unroll
   for (int q = 0; q < kTileCols / 32; ++q) bad_lut = bad_lut || (int)lut[q].x < c_lo || (int)lut[q].x > c_hi;
   bad_lut = __any_sync(0xffffffffu, bad_lut);
-  bool odd = bad_lut || c_hi - c_lo >= kMaxCellCols || !tp.src_tma_ok;
+  bool odd = bad_lut || c_hi - c_lo >= kMaxCellCols;
   float bx0 = 3e9f, bx1 = -3e9f, by0 = 3e9f, by1 = -3e9f;
   bool all_out = true;
   if (!odd) {
@@ -698,35 +698,57 @@ static bool encode_u32_rows(CUtensorMap *map, const void *base, size_t pitch, in
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-size_t warp_tile_scratch_bytes(int canvas_w, int n_blocks) {
+size_t warp_tiles_bytes(int canvas_w, int n_blocks) {
   const long long tiles = (long long)((canvas_w + kTileCols - 1) / kTileCols) * ((n_blocks + kTileBlocks - 1) / kTileBlocks);
   return (size_t)tiles * sizeof(TileInfo);
 }
 
-int launch_warp_tile(const WarpParams &w, const int *col_ext, bool words, void *scratch, size_t scratch_bytes, cudaStream_t st) {
+static int tile_counts(const WarpParams &w, TileParams &tp) {
+  tp.tiles_x = (w.canvas_w + kTileCols - 1) / kTileCols;
+  const long long tiles_y = (w.n_blocks + kTileBlocks - 1) / kTileBlocks;
+  if (tiles_y * tp.tiles_x > 2147483647LL) return fail(APAP_E_TOOBIG, "warp: too many tiles in one launch (split the band)");
+  tp.n_tiles = (int)(tiles_y * tp.tiles_x);
+  return 0;
+}
+
+// the tile records of a band (apap_warp_tiles); `w` needs the tables, the canvas and source geometry, no images
+int launch_warp_tiles(const WarpParams &w, const int *col_ext, void *tiles, size_t tiles_bytes, cudaStream_t st) {
   TileParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.w = w;
   tp.col_ext = reinterpret_cast<const int2 *>(col_ext);
+  const int rc = tile_counts(w, tp);
+  if (rc) return rc;
+  if (tp.n_tiles == 0) return 0;
+  if (!tiles || (reinterpret_cast<uintptr_t>(tiles) & 15u) || tiles_bytes < (size_t)tp.n_tiles * sizeof(TileInfo))
+    return fail(APAP_E_BADARG, "warp tiles: buffer missing, not 16-byte aligned or smaller than apap_warp_tiles_bytes()");
+  tp.tiles = static_cast<TileInfo *>(tiles);
+  k_tile_prep<<<(tp.n_tiles + 7) / 8, 256, 0, st>>>(tp);
+  return check_cuda(cudaGetLastError(), "k_tile_prep launch");
+}
+
+// can this source / band go through the tile engine?  (16-byte aligned source rows for the tensor maps)
+bool warp_tile_usable(const WarpParams &w) {
+  return ((size_t)w.src_w * 3) % 16 == 0 && !(reinterpret_cast<uintptr_t>(w.src) & 15u) && encode_tiled_fn() != nullptr;
+}
+
+int launch_warp_tile(const WarpParams &w, bool words, const void *tiles, cudaStream_t st) {
+  TileParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.w = w;
   tp.lab = getenv("APAP_TILE_LAB") ? atoi(getenv("APAP_TILE_LAB")) : 0;
   const size_t src_pitch = (size_t)w.src_w * 3;
-  tp.src_tma_ok = (src_pitch % 16 == 0) && !(reinterpret_cast<uintptr_t>(w.src) & 15u) && !w.force_exact;
-  if (getenv("APAP_TILE_NO_TMA")) tp.src_tma_ok = 0;      // lab switch: every tile gathers from global memory
-  for (int m = 0; m < kBoxShapes && tp.src_tma_ok; ++m)    // the source as uint32 [src_h][src_w * 3 / 4], three box shapes
+  for (int m = 0; m < kBoxShapes; ++m)                     // the source as uint32 [src_h][src_w * 3 / 4], three box shapes
     if (!encode_u32_rows(&tp.maps[m], w.src, src_pitch, w.src_h, box_w(m), box_h(m), CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
-      tp.src_tma_ok = 0;                                   // no tensor maps: every tile gathers from global memory
+      return fail(APAP_E_BADARG, "warp: cuTensorMapEncodeTiled refused the source image");
   // the band as uint32 [band_rows][canvas_w * 3 / 4], box 16 rows x 96 B
   const bool rows16 = (w.canvas_w % 16 == 0) && !(reinterpret_cast<uintptr_t>(w.out) & 15u) && !w.multicast &&
                       encode_u32_rows(&tp.out_map, w.out, (size_t)w.canvas_w * 3, w.band_rows, kWarpPitch, kWarpRows,
                                       CU_TENSOR_MAP_L2_PROMOTION_NONE);
   tp.store_mode = w.multicast ? 3 : rows16 ? 2 : words ? 1 : 0;
-  tp.tiles_x = (w.canvas_w + kTileCols - 1) / kTileCols;
-  const long long tiles_y = (w.n_blocks + kTileBlocks - 1) / kTileBlocks;
-  if (tiles_y * tp.tiles_x > 2147483647LL) return fail(APAP_E_TOOBIG, "warp: too many tiles in one launch (split the band)");
-  tp.n_tiles = (int)(tiles_y * tp.tiles_x);
-  if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 15u) || scratch_bytes < (size_t)tp.n_tiles * sizeof(TileInfo))
-    return fail(APAP_E_BADARG, "warp: tile scratch missing, not 16-byte aligned or smaller than apap_warp_scratch_bytes()");
-  tp.tiles = static_cast<TileInfo *>(scratch);
+  const int rc = tile_counts(w, tp);
+  if (rc) return rc;
+  tp.tiles = const_cast<TileInfo *>(static_cast<const TileInfo *>(tiles));
   static bool configured[64] = {};                         // > 48 KB of dynamic shared memory is opt-in, per device
   const size_t smem = sizeof(TileSmem);
   int dev = 0;
@@ -742,7 +764,6 @@ int launch_warp_tile(const WarpParams &w, const int *col_ext, bool words, void *
   const int grid = min(tp.n_tiles, sm_count_cached() * APAP_TILE_CTAS);
   static std::atomic<unsigned> launch_seq{0};              // concurrent launches (other streams) get different counters
   tp.slot = (int)(launch_seq.fetch_add(1u) % kCounterSlots);
-  k_tile_prep<<<(tp.n_tiles + 7) / 8, 256, 0, st>>>(tp);
   if (w.centre) k_warp_tile<true><<<grid, kTileThreads, smem, st>>>(tp);
   else k_warp_tile<false><<<grid, kTileThreads, smem, st>>>(tp);
   return check_cuda(cudaGetLastError(), "k_warp_tile launch");

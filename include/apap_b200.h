@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 15
+#define APAP_ABI_VERSION 16
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -135,26 +135,25 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
  *               path, g > 1 = the whole cell maps outside the source image and is left black
  *   cell_hinv : float [grid_rows*grid_cols][9], the inverted grid of pyviz/apap.py:201-203
  *   col_lut   : uint32 [canvas_w][2] = {cell column, float32 bits of dx}
- *   col_extent: int32 [grid_cols][2] = {first, last} canvas column of the cell column (the array apap_warp_tables
- *               takes); the tile engine bounds a tile's source footprint with it (unused by APAP_WARP_LEGACY)
  *   row_blocks: uint32 [n_blocks][2] = {first canvas row | rows << 28 (rows = 1..APAP_WARP_BLOCK_ROWS),
  *               cell row | dy of the first row << 16}, in canvas order and contiguous (block k+1 starts at or
  *               before the row after block k's last); a block never crosses a cell row; the blocks passed are
  *               the rows that get written (a row band of a sharded run = its blocks); canvas rows < 2^28, cell
  *               rows and dy < 2^16
  *   row0, row1: out_band holds the canvas rows [row0, row1); every row block lies inside
- *   out_band  : uint8 [row1 - row0][canvas_w][3], out_band_bytes >= that and < 2 GiB.  Rows leave the kernel as
- *               TMA bulk stores when the band is 16-byte aligned and canvas_w % 16 == 0, as 32-bit stores when
- *               4-byte aligned and canvas_w % 4 == 0, else as byte stores
+ *   out_band  : uint8 [row1 - row0][canvas_w][3], out_band_bytes >= that and < 2 GiB
  *   centre    : optional uint8 [centre_h][centre_w][3] pasted at (off_x, off_y) and blended with
  *               the warped pixel by the uniform_blend rule (fused K3+K4, pyviz/apap.py:259-261);
  *               NULL = plain warp
  *   flags     : APAP_WARP_FORCE_EXACT = every pixel takes the float64 path (validation switch);
- *               APAP_WARP_LEGACY = the strip kernel of round 1 (one warp per 32 columns, gathers from global
- *               memory, shuffle re-pack) instead of the tile engine (csrc/warp_tile.cu: the source footprint of
- *               a 128 x 32 canvas tile staged in shared memory with TMA bulk copies, LDS gathers, the output
- *               tile assembled in shared memory and stored as whole row segments).  Same bytes either way.
- *   scratch   : device scratch of at least apap_warp_scratch_bytes(canvas_w, n_blocks) bytes (see below)
+ *               APAP_WARP_LEGACY = the strip kernel even when `tiles` is given
+ *   tiles     : the band's tile records from apap_warp_tiles (same tables, same band), or NULL.  With tiles, and a
+ *               source whose rows are 16-byte aligned (src % 16 == 0, src_w * 3 % 16 == 0), the TILE ENGINE runs
+ *               (csrc/warp_tile.cu): persistent warp-specialised CTAs; per 128 x 32 canvas tile the source box the
+ *               tile can pick from is staged in shared memory by one tensor-map TMA copy (zero outside the image),
+ *               gathers are LDS, the output leaves as 16-row tensor-map TMA stores when the band is 16-byte aligned
+ *               and canvas_w % 16 == 0.  Otherwise the STRIP KERNEL of round 1 runs (one warp per 32 columns,
+ *               gathers from global memory, shuffle re-pack).  Same bytes either way.
  *   multicast   : non-zero = out_band is an NVLS multicast address (one mapping of the same panorama buffer on every
  *                 GPU of the group, e.g. torch symmetric memory's multicast_ptr + band offset): the kernel stores with
  *                 multimem.st, so the NVSwitch writes this rank's row band into every GPU's panorama -- the panorama
@@ -165,18 +164,25 @@ int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int 
 #define APAP_WARP_FORCE_EXACT 1
 #define APAP_WARP_LEGACY      2
 int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
-              const uint32_t *col_lut, const int *col_extent, const uint32_t *row_blocks, int n_blocks,
+              const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks,
               int grid_cols, int canvas_w, int off_x, int off_y, int row0, int row1,
               const uint8_t *centre, int centre_h, int centre_w,
               uint8_t *out_band, size_t out_band_bytes, int flags, int multicast,
-              void *scratch, size_t scratch_bytes, void *stream);
+              const void *tiles, void *stream);
+
 /*
- * Device scratch apap_warp needs for a band of n_blocks row blocks on a canvas_w wide canvas (the tile engine's
- * per-tile records: which source box a 128 x 32 canvas tile gathers from, its rows by cell row; 192 bytes per
- * tile, written by a preparation kernel at the start of every call).  16-byte aligned, caller-owned, may be reused
- * by the next call on the same stream; APAP_WARP_LEGACY does not touch it (NULL / 0 allowed).
+ * The tile engine's per-tile records for a band: for every 128-column x 8-row-block tile of the canvas, the source
+ * box its pixels can pick from (the corners of every cell x tile rectangle mapped through the cell's H^-1), the
+ * tensor-map box shape, its rows grouped by cell row, and whether it is all black.  They depend on the tables and
+ * the geometry only -- not on the images -- so they are built once per inverted grid and band (with
+ * apap_warp_tables) and reused by every apap_warp call on it.
+ *   col_extent : int32 [grid_cols][2] = {first, last} canvas column of the cell column (as for apap_warp_tables)
+ *   tiles      : out, 16-byte aligned, apap_warp_tiles_bytes(canvas_w, n_blocks) bytes (192 per tile)
  */
-int apap_warp_scratch_bytes(int canvas_w, int n_blocks, size_t *bytes);
+int apap_warp_tiles_bytes(int canvas_w, int n_blocks, size_t *bytes);
+int apap_warp_tiles(const float *cell_fast, const float *cell_hinv, const uint32_t *col_lut, const int *col_extent,
+                    const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x, int off_y,
+                    int src_h, int src_w, void *tiles, size_t tiles_bytes, void *stream);
 
 /*
  * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,
