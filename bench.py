@@ -108,80 +108,154 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU baselines
-def _cpu_cells_worker(args):
-    name, seed, cells = args
+# The reference's own CPU implementation of the path on the box's host cores.  When ``oracle/_ref/pyviz`` holds the
+# reference's scripts (oracle/make_ref.py, run by build() in the build container) the workers call the REAL
+# ``APAP.local_homography`` / ``APAP.local_warp`` of pyviz/apap.py (kind "reference"); otherwise the oracle's
+# restatement of the same per-cell loop (kind "port").  One persistent pool of worker processes, every worker builds
+# its scene once; only the workers' compute loop is inside the timed wall.
+_REF = {}
+
+
+def _ref_init(name):
+    """Pool initialiser: the scene, the reference module (or the port) and an H grid for the warp sample."""
+    import contextlib
+    import io
     from cvx_proj_b200 import synth
     from oracle import apap_oracle as orc
-    sc = synth.make_scene(name, seed=seed)
+    from oracle import make_ref
+    sc = synth.make_scene(name)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = make_ref.load()
+    _REF.update(sc=sc, ref=ref, orc=orc, img=None, h_rows=None)
+
+
+def _ref_cells(rows):
+    """``local_homography`` on the cell rows ``rows`` (a slice of the vertex grid): seconds of compute."""
+    sc, ref, orc = _REF["sc"], _REF["ref"], _REF["orc"]
+    verts = np.ascontiguousarray(sc.vertices[rows[0]:rows[1]])
     t0 = time.perf_counter()
-    orc.local_homography_svd(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma, cells=cells)
+    if ref is not None:
+        st = ref.APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y])
+        st.local_homography(sc.src, sc.dst, verts)
+    else:
+        orc.local_homography_svd(sc.src, sc.dst, verts, sc.gamma, sc.sigma)
     return time.perf_counter() - t0
 
 
-def cpu_moving_dlt(name, n_cells, procs):
-    """The oracle's per-cell weighted-SVD loop (the reference's algorithm, pyviz/apap.py:147-168) on
-    ``n_cells`` evenly spread cells of the workload, split over ``procs`` worker processes."""
-    import multiprocessing as mp
-    from cvx_proj_b200 import synth
-    mesh = synth.CONFIGS[name]["mesh"]
-    pick = np.linspace(0, mesh * mesh - 1, n_cells).astype(np.int64)
-    cells = [(int(c // mesh), int(c % mesh)) for c in pick]
-    chunks = [cells[k::procs] for k in range(procs)]
-    ctx = mp.get_context("fork")
+def _ref_warp(n_rows):
+    """``local_warp`` on the first ``n_rows`` canvas rows (the cell rows they touch): seconds of compute."""
+    import contextlib
+    import io
+    sc, ref, orc = _REF["sc"], _REF["ref"], _REF["orc"]
+    if _REF["img"] is None:
+        _REF["img"] = sc.image(1)
+        k = int(np.searchsorted(sc.mesh[1], n_rows, side="left")) + 1          # cell rows under the sampled canvas rows
+        sub = np.ascontiguousarray(sc.vertices[:k, ::max(1, sc.mesh_cells // 8)])
+        h_small = orc.local_homography_gram64(sc.src, sc.dst, sub, sc.gamma, sc.sigma)
+        reps = -(-sc.mesh_cells // h_small.shape[1])
+        _REF["h_rows"] = np.repeat(h_small, reps, 1)[:, :sc.mesh_cells].astype(np.float32).copy()
+    img, h = _REF["img"], _REF["h_rows"].copy()
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_cells_worker, [(name, 0, ch) for ch in chunks if ch])
-    wall = time.perf_counter() - t0
-    return n_cells / wall, wall
+    if ref is not None:
+        st = ref.APAP(sc.gamma, sc.sigma, [sc.final_w, n_rows], [sc.offset_x, sc.offset_y])
+        with contextlib.redirect_stdout(io.StringIO()):
+            st.local_warp(img, h, sc.mesh)
+    else:
+        orc.local_warp(img, orc.invert_grid(h), sc.mesh, (sc.final_w, n_rows), (sc.offset_x, sc.offset_y))
+    return time.perf_counter() - t0
 
 
-def cpu_warp(name, n_rows):
-    """The oracle's vectorised float64 restatement of the pixel loop (pyviz/apap.py:206-215) on the
-    first ``n_rows`` canvas rows of the workload (single process, numpy)."""
-    from cvx_proj_b200 import synth
-    from oracle import apap_oracle as orc
-    sc = synth.make_scene(name)
-    img = sc.image(1)
-    sub = sc.vertices[::max(1, sc.mesh_cells // 8), ::max(1, sc.mesh_cells // 8)]
-    h_small = orc.local_homography_gram64(sc.src, sc.dst, sub, sc.gamma, sc.sigma)
-    reps = -(-sc.mesh_cells // h_small.shape[0])
-    h = np.repeat(np.repeat(h_small, reps, 0), reps, 1)[:sc.mesh_cells, :sc.mesh_cells].copy()
-    inv = orc.invert_grid(h)
-    n_rows = min(n_rows, sc.final_h)
-    t0 = time.perf_counter()
-    orc.local_warp(img, inv, sc.mesh, (sc.final_w, n_rows), (sc.offset_x, sc.offset_y))
-    wall = time.perf_counter() - t0
-    return sc.final_w * n_rows / wall / 1e6, wall
+class ReferencePool:
+    """``procs`` worker processes holding the workload's scene; ``dlt(rows_per_proc)`` / ``warp(n_rows)`` time one
+    bounded sample each (wall clock around the pool call, the workers only compute)."""
+
+    def __init__(self, name, procs):
+        import multiprocessing as mp
+        from cvx_proj_b200 import synth
+        from oracle import make_ref
+        self.name, self.procs = name, procs
+        self.cfg = synth.CONFIGS[name]
+        self.kind = "reference" if all(os.path.exists(os.path.join(make_ref.DST, f)) for f in make_ref.FILES) else "port"
+        self.pool = mp.get_context("fork").Pool(procs, initializer=_ref_init, initargs=(name,))
+        self.pool.map(_ref_cells, [(0, 0)] * procs)            # every worker is up and has its scene
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def dlt(self, rows_per_proc):
+        """Every worker solves ``rows_per_proc`` whole cell rows, the workers' rows spread evenly over the grid.
+        Returns (cells, wall seconds)."""
+        mesh = self.cfg["mesh"]
+        rows_per_proc = max(1, min(rows_per_proc, mesh // self.procs))
+        starts = np.linspace(0, mesh - rows_per_proc, self.procs).astype(int)
+        t0 = time.perf_counter()
+        self.pool.map(_ref_cells, [(int(a), int(a) + rows_per_proc) for a in starts])
+        self.rows_used = rows_per_proc
+        return self.procs * rows_per_proc * mesh, time.perf_counter() - t0
+
+    def warp(self, seconds):
+        """Every worker warps the first canvas rows (P identical samples, about ``seconds`` of wall at the reference's
+        ~0.13 Mpix/s per process).  Returns (pixels, wall seconds)."""
+        from cvx_proj_b200 import synth
+        sc = synth.make_scene(self.name)
+        n_rows = self.warp_rows = int(max(2, min(sc.final_h, seconds * 0.13e6 / sc.final_w)))
+        t0 = time.perf_counter()
+        self.pool.map(_ref_warp, [n_rows] * self.procs)
+        return self.procs * n_rows * sc.final_w, time.perf_counter() - t0
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("the reference itself (oracle/_ref/pyviz/apap.py, unmodified): APAP.local_homography on disjoint "
+                    f"cell-row slices in {self.procs} worker processes")
+        return (f"oracle port of the reference's per-cell weighted-SVD loop (cv.SVDecomp float64) in {self.procs} "
+                "worker processes (oracle/_ref absent)")
+
+
+def _rows_for_seconds(pool, seconds):
+    """Cell rows per worker for about ``seconds`` of wall per step, from one timed row per worker on this box."""
+    _, wall = pool.dlt(1)
+    return max(1, int(seconds / max(wall, 1e-3)))
+
+
+def _config(name, world):
+    """The ``config`` object of the bench line: the same for both arms."""
+    return {"workload": _workload_desc(name), "per_rank": "one pair per GPU (independent pairs)" if world > 1 else "one pair",
+            "l2": "GPU arm: flushed before every timed step (256 MiB write); CPU arm: n/a"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm for the path (oracle port: the reference is
-    pure Python and cannot travel to the GPU box) on all host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, a bounded sample of the
+    workload per step (persistent worker pool, scenes prebuilt: only the workers' loops are timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     name = args.workload or "c2"
     procs = os.cpu_count() or 1
-    from cvx_proj_b200 import synth
-    cfg = synth.CONFIGS[name]
-    per_cell_s = 2.0e-3 * cfg["n_kp"] / 5000 + 3e-4
-    # bounded sample: ~2 s of wall per step on this box's cores
-    n_cells = int(min(cfg["mesh"] ** 2, max(4 * procs, 2.0 * procs / per_cell_s)))
-    times = []
+    pool = ReferencePool(name, procs)
+    rows = _rows_for_seconds(pool, 2.0)                           # ~2 s of wall per step
+    walls, cells = [], 0
     for k in range(args.warmup + args.steps):
-        rate, wall = cpu_moving_dlt(name, n_cells, procs)
+        cells, wall = pool.dlt(rows)
         if k >= args.warmup:
-            times.append(wall)
-    ms = 1e3 * float(np.mean(times))
-    value = n_cells / (ms * 1e-3)
-    sample = (f"{n_cells} of {cfg['mesh'] ** 2} cells of {name} per step (evenly spread), oracle per-cell "
-              f"weighted SVD (cv.SVDecomp, float64) in {procs} worker processes")
+            walls.append(wall)
+    wpx, wwall = pool.warp(1.0)
+    pool.close()
+    rows = pool.rows_used
+    ms = 1e3 * float(np.mean(walls))
+    value = cells / (ms * 1e-3)
+    total = pool.cfg["mesh"] ** 2
+    sample = f"{cells} of {total} cells of {name} per step ({rows} whole cell rows per worker, spread evenly); {pool.describe()}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": _workload_desc(name)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "config": _config(name, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": pool.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "warp": {"metric": "apap_mesh_warp_mpix_per_s", "value": wpx / wwall / 1e6, "unit": "Mpix/s", "cores": procs,
+                     "kind": pool.kind,
+                     "sample": f"the first {pool.warp_rows} canvas rows of {name} in each of {procs} workers (APAP.local_warp's "
+                               f"pixel loop and the per-cell inverses of the cell rows under them), {wwall:.1f} s wall"},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -282,9 +356,9 @@ class Pass:
         self.pasted = torch.zeros_like(self.canvas)
         self.host_img, self.host_centre = img, centre
 
-    def warp(self, fused=False):
+    def warp(self, fused=False, legacy=False):
         self.st.warp_device(self.img, self.tables, self.sc.mesh_cells, centre_dev=self.centre if fused else None,
-                            out=self.canvas)
+                            out=self.canvas, legacy=legacy)
 
     def blend(self):
         self.rt.blend_device(self.torch, self.canvas, self.pasted, out=self.canvas2)
@@ -375,11 +449,12 @@ def run_ours(args):
     p.prepare_warp()
     barrier()
     (t_warp,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(False), mark()), 2)
+    (t_strip,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(False, legacy=True), mark()), 2)
     (t_fused,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.warp(True), mark()), 2)
     (t_blend,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), p.blend(), mark()), 2)
     barrier()
-    launches += 3 * K
-    ms_warp, ms_fused, ms_blend = (max_over_ranks(t) for t in (t_warp, t_fused, t_blend))
+    launches += 4 * K
+    ms_warp, ms_fused, ms_blend, ms_strip = (max_over_ranks(t) for t in (t_warp, t_fused, t_blend, t_strip))
     canvas_px = sc.canvas_px
     src_px = sc.width * sc.height
     warp_bytes = 3 * canvas_px + 3 * src_px                       # write canvas once + read source once
@@ -447,6 +522,11 @@ def run_ours(args):
         c3 = run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks, barrier, args.gram_engine)
         launches += c3.pop("_launches")
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = run_c4_c5(torch, device, flush, mufu_peak * 1e12)
+        launches += extras.pop("_launches")
+
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -457,14 +537,21 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
-        n_cells = int(min(sc.n_cells, max(4 * procs, 30.0 / (2.5e-3 * sc.src.shape[0] / 5000 + 3e-4))))   # ~20-30 s of CPU work
-        rate, wall = cpu_moving_dlt(name, n_cells, procs)
-        wrate, wwall = cpu_warp(name, 256)
-        cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": (f"{n_cells} of {sc.n_cells} cells of {name} (evenly spread), oracle per-cell weighted SVD "
-                          f"(cv.SVDecomp float64, the reference's algorithm) over {procs} processes, {wall:.1f} s wall"),
-               "warp": {"value": wrate, "unit": "Mpix/s", "cores": 1,
-                        "sample": f"first 256 canvas rows of {name}, oracle vectorised float64 numpy, {wwall:.1f} s"}}
+        pool = ReferencePool(name, procs)
+        rows = _rows_for_seconds(pool, 2.0)                         # the reference arm's step, five times: ~10 s of CPU work
+        n_cells, wall = 0, 0.0
+        for _ in range(5):
+            c, w = pool.dlt(rows)
+            n_cells, wall = n_cells + c, wall + w
+        wpx, wwall = pool.warp(3.0)
+        pool.close()
+        rows = pool.rows_used
+        cpu = {"value": n_cells / wall, "unit": UNIT, "cores": procs, "kind": pool.kind,
+               "sample": (f"5 x {n_cells // 5} of {sc.n_cells} cells of {name} ({rows} whole cell rows per worker, spread evenly), "
+                          f"{pool.describe()}, {wall:.1f} s wall"),
+               "warp": {"value": wpx / wwall / 1e6, "unit": "Mpix/s", "cores": procs, "kind": pool.kind,
+                        "sample": f"the first {pool.warp_rows} canvas rows of {name} in each of {procs} workers (APAP.local_warp), "
+                                  f"{wwall:.1f} s wall"}}
 
     pairs = float(p.n_pad) * p.cells                                          # (cell, keypoint) pairs per launch
     gram_flops = 2.0 * 24 * pairs
@@ -479,7 +566,8 @@ def run_ours(args):
         roof = {"kernel": "k_gram_tc", "bound": "xu",
                 "achieved": 2.0 * pairs / gram_s / 1e12, "peak": mufu_peak, "unit": "Tlane-op/s",
                 "frac": 2.0 * pairs / gram_s / 1e12 / mufu_peak, "traffic": next((v for k, v in traffic.items() if k.startswith("k_gram_tc")), None),
-                "peak_source": "MUFU.EX2 probe kernel timed in this run (not in MEASURED_PEAKS.json)",
+                "peak_source": "MUFU.EX2 probe kernel timed in this run (MEASURED_PEAKS.json has no XU figure); it equals the "
+                               "nominal 148 SM x 16 lanes x SM clock",
                 "algorithmic": "2 transcendental evaluations (sqrt, exp2) per (cell, keypoint) pair, the XU pipe's work in "
                                "the plain kernel; the contraction itself runs on the tensor pipe",
                 "executed_mufu_per_pair": 1.5 if sc.gamma >= 0.5 else 2.0,
@@ -490,6 +578,11 @@ def run_ours(args):
                            "what": "executed TF32 MMA flop (3xTF32, N padded to 32) against bf16_tflops / 2 "
                                    "of MEASURED_PEAKS.json"},
                 "fp32_equivalent": fp32_equiv, "ms": ms_gram, "eig_ms": ms_eig,
+                "fractions": {"xu_algorithmic": 2.0 * pairs / gram_s / 1e12 / mufu_peak,
+                              "xu_executed": (1.5 if sc.gamma >= 0.5 else 2.0) * pairs / gram_s / 1e12 / mufu_peak,
+                              "tensor_executed_tf32": mma_flops / gram_s / 1e12 / tf32_peak,
+                              "tensor_algorithmic_24_terms": gram_flops / gram_s / 1e12 / tf32_peak,
+                              "fp32_equivalent": fp32_equiv["frac"]},
                 "stage_note": "ms / eig_ms: K1 and K2 launched and timed one by one; the stage (ms_per_step, value) is the "
                               "public call's launch, K2 a programmatic dependent of K1 that starts on finished cell tiles"}
     else:
@@ -502,10 +595,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dlt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32x3+f32" if args.gram_engine == "tcgen05" else "f32", "data": "synthetic",
-        "config": {"workload": _workload_desc(name), "per_rank": "one pair per GPU (independent pairs)",
-                   "l2": "flushed before every timed step (256 MiB write)", "cells": p.cells,
-                   "n_kp_padded": p.n_pad, "k_splits": p.k_splits, "canvas": [sc.final_w, sc.final_h],
-                   "gram_engine": args.gram_engine},
+        "config": _config(name, world),
+        "setup": {"cells": p.cells, "n_kp_padded": p.n_pad, "k_splits": p.k_splits, "canvas": [sc.final_w, sc.final_h],
+                  "gram_engine": args.gram_engine},
         "roofline": roof,
         "e2e": {"value": cells_total / e2e_dlt_s, "unit": UNIT, "h2d_bytes_per_step": h2d_dlt,
                 "d2h_bytes_per_step": d2h_dlt, "ms_per_step": e2e_dlt_s * 1e3,
@@ -513,10 +605,13 @@ def run_ours(args):
         "warp": {
             "metric": "apap_mesh_warp_mpix_per_s", "value": world * canvas_px / (ms_warp * 1e-3) / 1e6, "unit": "Mpix/s",
             "ms_per_step": ms_warp, "dtype": "u8",
-            "roofline": {"kernel": "k_warp", "bound": "hbm", "achieved": warp_bytes / (ms_warp * 1e-3) / 1e9,
+            "roofline": {"kernel": "k_warp_tile", "bound": "hbm", "achieved": warp_bytes / (ms_warp * 1e-3) / 1e9,
                          "peak": hbm, "unit": "GB/s", "frac": warp_bytes / (ms_warp * 1e-3) / 1e9 / hbm,
-                         "traffic": traffic.get("k_warp<0, 1>"), "peak_source": peak_src,
-                         "algorithmic": "3*canvas_px + 3*src_px bytes per launch"},
+                         "traffic": next((v for k, v in traffic.items() if k.startswith("k_warp_tile")), None),
+                         "peak_source": peak_src, "algorithmic": "3*canvas_px + 3*src_px bytes per launch",
+                         "strip_kernel_ms": ms_strip,
+                         "note": "tile engine (tensor-map TMA source boxes in shared memory, LDS gathers, TMA row stores); "
+                                 "strip_kernel_ms = round 1's kernel on the same tables in the same run"},
             "fused_warp_blend": {"ms_per_step": ms_fused, "mpix_per_s": canvas_px / (ms_fused * 1e-3) / 1e6,
                                  "hbm_frac": fused_bytes / (ms_fused * 1e-3) / 1e9 / hbm},
             "blend": {"ms_per_step": ms_blend, "mpix_per_s": canvas_px / (ms_blend * 1e-3) / 1e6,
@@ -547,6 +642,9 @@ def run_ours(args):
     }
     if c3 is not None:
         line["c3_sharded"] = c3
+    if extras is not None:
+        line["c4_batch"] = extras["c4"]
+        line["c5_sweep"] = extras["c5"]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -583,7 +681,7 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
         (t_gather,) = timed_steps(torch, flush, W, K, gather_body, 2)
         barrier()
     # the panorama assembled by the warp kernel itself: row band stored into every GPU through the NVLS multicast mapping
-    ms_fused, assembled_ok = None, None
+    ms_fused, assembled_ok, assemble_variants = None, None, None
     if world > 1:
         try:
             sym = sharding.SymmetricPanorama(sc0.final_h, sc0.final_w, device)
@@ -602,7 +700,20 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
                 mark()
             (t_fused,) = timed_steps(torch, flush, W, K, fused_body, 2)
             barrier()
-            ms_fused = max_over_ranks(t_fused)
+            ms_bcast = max_over_ranks(t_fused)
+
+            def direct_body(mark):
+                mark()
+                # ONE kernel: the tile engine stores its tiles' 384-byte rows straight into the multicast mapping
+                p.st.warp_device(p.img, p.tables, p.sc.mesh_cells, multicast_ptr=sym.band_ptr(me.px_row0))
+                sym.barrier()
+                mark()
+            sym.barrier()
+            (t_direct,) = timed_steps(torch, flush, W, K, direct_body, 2)
+            barrier()
+            ms_direct = max_over_ranks(t_direct)
+            ms_fused = min(ms_bcast, ms_direct)
+            assemble_variants = {"warp_then_broadcast_kernel_ms": ms_bcast, "warp_kernel_multicast_stores_ms": ms_direct}
             # every band of this rank's panorama must be the band its owner warped (checksums travel over NCCL)
             def checksum(t):
                 v = t.reshape(-1).to(torch.int64)
@@ -616,17 +727,96 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
     ms_dlt = max_over_ranks(t_dlt)
     ms_warp = max_over_ranks(t_warp)
     ms_gather = max_over_ranks(t_gather)
+    # the same pass on ONE GPU of this box in this run (every rank times the whole grid / canvas on its own GPU)
+    one = {"dlt_ms": ms_dlt, "warp_ms": ms_warp}
+    if world > 1:
+        del p
+        torch.cuda.empty_cache()
+        pf = Pass(torch, device, "c3", seed=0, gram_engine=gram_engine)
+        (t1_dlt,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), pf.dlt(), mark()), 2)
+        pf.prepare_warp()
+        (t1_warp,) = timed_steps(torch, flush, W, K, lambda mark: (mark(), pf.warp(False), mark()), 2)
+        barrier()
+        one = {"dlt_ms": max_over_ranks(t1_dlt), "warp_ms": max_over_ranks(t1_warp)}
+    eff = {"dlt": one["dlt_ms"] / (world * ms_dlt), "warp": one["warp_ms"] / (world * ms_warp)}
+    if ms_fused:
+        eff["warp_and_assemble"] = one["warp_ms"] / (world * ms_fused)
     return {"workload": _workload_desc("c3"), "scaling": "strong", "n_gpus": world,
+            "one_gpu_same_run": one, "efficiency_vs_1gpu": eff,
+            "limiter": ("DLT: K1 is XU-bound and shards without exchange; the sharded grid has fewer cell tiles per SM wave. "
+                        "Warp: the band kernel is a few tens of microseconds, launch latency and the fixed prologue do not shrink "
+                        "with N. Assembly: every GPU receives (N-1)/N of the 124 MB panorama over NVLink whatever the method "
+                        "(>= 150 us at the ~750 GB/s a B200 takes in)"),
             "cells_per_s": sc0.n_cells / (ms_dlt * 1e-3), "dlt_ms": ms_dlt, "gram_ms": max_over_ranks(t_gram),
             "warp_mpix_per_s": sc0.canvas_px / (ms_warp * 1e-3) / 1e6, "warp_ms": ms_warp,
             "allgather_ms": ms_gather, "allgather_bytes": 3 * sc0.canvas_px,
-            "warp_and_assemble_ms": ms_fused, "assembled_panorama_verified_on_every_rank": assembled_ok,
+            "warp_and_assemble_ms": ms_fused, "warp_and_assemble_variants": assemble_variants,
+            "assembled_panorama_verified_on_every_rank": assembled_ok,
             "warp_and_assemble_note": "warp into the rank's panorama (symmetric memory) + broadcast of the band into every "
                                       "other GPU's panorama (NVLS multimem.st kernel; a peer copy at 2 GPUs) + group barrier: "
                                       "replaces warp_ms + allgather_ms; null without NVSwitch multicast. Every GPU receives "
                                       "(N-1)/N of the panorama over NVLink either way",
             "shard": "cell rows + canvas row bands per rank; keypoints and source image replicated",
-            "_launches": 5 * K}
+            "_launches": 5 * K + (3 * K if world > 1 else 0)}
+
+
+def run_c4_c5(torch, device, flush, mufu_peak):
+    """BASELINE configs c4 (a batch of 64 1080p pairs, 2k keypoints, 100 x 100 grid, ONE launch of K1 + K2) and c5
+    (keypoint sweep at a fixed 256 x 256 grid) on one GPU: device-resident, CUDA events, L2 flushed before every launch."""
+    from cvx_proj_b200 import _runtime as rt, synth
+    from cvx_proj_b200.apap import APAP, scale_anchors, weight_scale
+
+    def timed(fn, iters=5, warm=3):
+        ts = []
+        for k in range(iters + warm):
+            flush.add_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            if k >= warm:
+                ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    def tensors(sc, st):
+        table, tmats = st._prepare(sc.src, sc.dst)
+        return table, tmats, scale_anchors(sc.vertices, weight_scale(sc.sigma))
+
+    launches, sweep = 0, []
+    for n_kp in (1000, 4000, 16000, 64000):
+        sc = synth.make_scene("c5", n_kp=n_kp)
+        st = APAP(sc.gamma, sc.sigma, [sc.final_w, sc.final_h], [sc.offset_x, sc.offset_y], device=device)
+        table, tmats, anchors = tensors(sc, st)
+        t_dev = st.kp_table_device(torch.from_numpy(table[None]).to(device))
+        a_dev, m_dev = torch.from_numpy(anchors[None]).to(device), torch.from_numpy(tmats[None]).to(device)
+        cells, n_pad = sc.n_cells, table.shape[0]
+        ks, _, nbytes = rt.gram_plan(cells, n_pad, rt.GRAM_TCGEN05)
+        partials = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        out_h = torch.empty((1, cells, 9), dtype=torch.float32, device=device)
+        lib, stream = rt.load_library(), rt.stream_ptr(torch, device)
+        g2 = float(np.float32(sc.gamma ** 2))
+        ms_gram = timed(lambda: rt.check(lib.apap_gram_partials(t_dev.data_ptr(), a_dev.data_ptr(), 1, cells, n_pad, g2,
+                                                                rt.GRAM_TCGEN05, partials.data_ptr(), stream)))
+        ms_both = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, 1, cells, out_h=out_h, partials=partials))
+        launches += 8 * 3
+        sweep.append({"n_kp": n_kp, "cells": cells, "k_splits": ks, "gram_ms": ms_gram, "k1_k2_ms": ms_both,
+                      "cells_per_s": cells / (ms_both * 1e-3), "xu_frac": 2.0 * cells * n_pad / (ms_gram * 1e-3) / mufu_peak})
+    pairs = 64
+    scs = [synth.make_scene("c4", seed=k) for k in range(pairs)]
+    st = APAP(scs[0].gamma, scs[0].sigma, [scs[0].final_w, scs[0].final_h], [scs[0].offset_x, scs[0].offset_y], device=device)
+    prep = [tensors(sc, st) for sc in scs]
+    rows = torch.from_numpy(np.stack([q[0] for q in prep])).to(device)
+    t_dev = st.kp_table_device(rows)
+    m_dev = torch.from_numpy(np.stack([q[1] for q in prep])).to(device)
+    a_dev = torch.from_numpy(np.stack([q[2] for q in prep])).to(device)
+    cells, n_pad = scs[0].n_cells, rows.shape[1]
+    _, _, nbytes = rt.gram_plan(cells, n_pad, rt.GRAM_TCGEN05)
+    partials = torch.empty(pairs * nbytes // 4, dtype=torch.float32, device=device)
+    out_h = torch.empty((pairs, cells, 9), dtype=torch.float32, device=device)
+    ms_batch = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, pairs, cells, out_h=out_h, partials=partials))
+    launches += 8 * 2
+    c4 = {"workload": _workload_desc("c4") + f", batch of {pairs} pairs in one launch", "batch_ms": ms_batch,
+          "cells_per_s": pairs * cells / (ms_batch * 1e-3),
+          "xu_frac": 2.0 * pairs * cells * n_pad / (ms_batch * 1e-3) / mufu_peak}
+    return {"c4": c4, "c5": {"workload": "c5: 1920x1080 pair, 256x256 grid, keypoint sweep", "points": sweep}, "_launches": launches}
 
 
 def main():
@@ -636,8 +826,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c1..c5 (default c2)")
-    ap.add_argument("--c3", default="multi", choices=["multi", "always", ""],
-                    help="run the c3 sharded pass: with N>1 (default), always, or never ('')")
+    ap.add_argument("--c3", default="always", choices=["multi", "always", ""],
+                    help="run the c3 pass (strong-scaled over the ranks): always (default, N = 1 included), only with N>1, or never ('')")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c4 (batch of 64 pairs) and c5 (keypoint sweep) lines at N = 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--gram-engine", default="tcgen05", choices=["tcgen05", "ffma2"],
                     help="kernel of the moving-DLT contraction (default: tensor cores)")
