@@ -7,6 +7,7 @@ Tolerances (SURVEY.md section 8c / BASELINE.json north_star):
   local_weight (float64): relative 1e-13
 """
 import hashlib
+import os
 import zlib
 
 import numpy as np
@@ -815,3 +816,21 @@ def test_device_invert_grid_has_numpys_bits():
     bad[2] = 0
     with pytest.raises(np.linalg.LinAlgError):
         st.invert_grid(bad)
+
+
+def test_sharded_pass_over_nccl_two_gpus_is_bit_identical():
+    """Two ranks over NCCL (torchrun, one rank per GPU): the cell-row / row-band sharded pass equals the one-GPU pass
+    bit for bit -- H grid, all-gathered panorama, and the panorama assembled through the NVLS multicast mapping
+    (broadcast kernel and the warp kernel's own multimem stores).  tools/check_sharded_nccl.py is the rank program.
+    Skips on a box with fewer than two GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(repo, "tools", "check_sharded_nccl.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=repo)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "SHARDED NCCL CHECK PASSED" in res.stdout, res.stdout[-3000:]

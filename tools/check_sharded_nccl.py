@@ -37,7 +37,14 @@ for name, kw in (("mini", {}), ("c1", {}), ("c2", {})):
         fused = sh.local_warp_panorama(img, h_rows.copy(), sym)
         torch.cuda.synchronize()
         fused = fused.cpu().numpy()
-    same_f = True if fused is None else bool(np.array_equal(fused, pano))
+        direct = None
+        if sym.multicast_ptr:                   # the warp kernel's own multimem stores (whole tile rows) as well
+            sym.local.fill_(9)
+            dist.barrier()
+            direct = sh.local_warp_panorama(img, h_rows.copy(), sym, fused_stores=True)
+            torch.cuda.synchronize()
+            direct = direct.cpu().numpy()
+    same_f = True if fused is None else bool(np.array_equal(fused, pano) and (direct is None or np.array_equal(direct, pano)))
     flags = torch.tensor([int(same_f)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     same_f_all = bool(flags.item())
