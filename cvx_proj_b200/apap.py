@@ -623,29 +623,53 @@ class APAP:
         table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
         return table, tmats
 
-    def _upload_scene(self, torch, device, points, counts, anchors, tmats):
+    def _upload_scene(self, torch, device, points, counts, anchors):
         """One host->device copy for all kernel inputs of ``batch`` scenes: the arrays are packed into a pinned
         staging buffer (kept per instance) and sliced on the device.
-        Layout: float32 points [3, b, n, 2] (conditioned source, conditioned target, raw source) |
-        int32 counts [b] | float32 anchors [b, cells, 2] | float64 tmats [b, 18] (every section starts 16-byte
-        aligned).  Returns the keypoint ROW table built from the points on the device, the anchors, the matrices."""
+        Layout: float32 points [2, b, n, 2] (raw source, raw target) | int32 counts [b] | float32 anchors [b, cells, 2]
+        (every section starts 16-byte aligned).  The O(N) prologue of pyviz/apap.py:129-141 then runs on the device
+        (``apap_condition``).  Returns the keypoint ROW table built from the points on the device, the anchors, the
+        de-normalisation matrices."""
         if not hasattr(self, "_stage"):
             self._stage = _PinnedStage()
-        p_u8, c_u8, a_u8, m_u8 = self._stage.upload(torch, device, (points, counts, anchors, tmats))
-        rows = self.kp_rows_device(p_u8.view(torch.float32).view(points.shape), c_u8.view(torch.int32))
-        return rows, a_u8.view(torch.float32).view(anchors.shape), m_u8.view(torch.float64).view(tmats.shape)
+        p_u8, c_u8, a_u8 = self._stage.upload(torch, device, (points, counts, anchors))
+        raw = p_u8.view(torch.float32).view(points.shape)
+        counts_dev = c_u8.view(torch.int32)
+        cond, tmats = self.condition_device(raw, counts_dev)
+        rows = self.kp_rows_device((cond[0], cond[1], raw[0]), counts_dev)
+        return rows, a_u8.view(torch.float32).view(anchors.shape), tmats
+
+    def condition_device(self, raw_dev, counts_dev=None):
+        """``apap_condition``: the normalisers, conditioners and conditioned points of pyviz/apap.py:129-141 on the device.
+        ``raw_dev`` float32 ``[2, batch, n, 2]`` (source points, target points).  Returns ``(cond [2, batch, n, 2]
+        float32, tmats [batch, 18] float64)``; float64 reductions in a fixed order instead of numpy's float32 pairwise
+        sums, so H agrees with the host path (``_condition``) to ~1e-6 of the gate, not bit for bit."""
+        torch, device = rt.torch_cuda(raw_dev.device)
+        lib = rt.load_library()
+        _, batch, n, _ = raw_dev.shape
+        cond = torch.empty((2, batch, n, 2), dtype=torch.float32, device=device)
+        mats = torch.empty((batch, 36), dtype=torch.float32, device=device)
+        tmats = torch.empty((batch, 18), dtype=torch.float64, device=device)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_condition(raw_dev[0].data_ptr(), raw_dev[1].data_ptr(),
+                                        counts_dev.data_ptr() if counts_dev is not None else None, batch, n,
+                                        cond.data_ptr(), mats.data_ptr(), tmats.data_ptr(), rt.stream_ptr(torch, device)),
+                     "apap_condition")
+        return cond, tmats
 
     def kp_rows_device(self, points_dev, counts_dev=None):
         """Keypoint ROW table ``[batch, n_pad, 28]`` built on the device by ``apap_kp_rows`` (same bits as
-        ``build_kp_table``) from ``points_dev`` = float32 ``[3, batch, n, 2]``: conditioned source points,
-        conditioned target points, raw source points; ``counts_dev`` int32 ``[batch]`` = matches per scene."""
-        torch, device = rt.torch_cuda(points_dev.device)
+        ``build_kp_table``) from ``points_dev`` = float32 ``[3, batch, n, 2]`` (or a tuple of three ``[batch, n, 2]``
+        tensors): conditioned source points, conditioned target points, raw source points; ``counts_dev`` int32
+        ``[batch]`` = matches per scene."""
+        cf1, cf2, raw = points_dev[0], points_dev[1], points_dev[2]
+        torch, device = rt.torch_cuda(cf1.device)
         lib = rt.load_library()
-        _, batch, n, _ = points_dev.shape
+        batch, n, _ = cf1.shape
         n_pad = max(KP_CHUNK, (n + KP_CHUNK - 1) // KP_CHUNK * KP_CHUNK)
         rows = torch.empty((batch, n_pad, KP_ROW), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
-            rt.check(lib.apap_kp_rows(points_dev[0].data_ptr(), points_dev[1].data_ptr(), points_dev[2].data_ptr(),
+            rt.check(lib.apap_kp_rows(cf1.data_ptr(), cf2.data_ptr(), raw.data_ptr(),
                                       counts_dev.data_ptr() if counts_dev is not None else None, batch, n, n_pad,
                                       weight_scale(self.sigma), rows.data_ptr(), rt.stream_ptr(torch, device)),
                      "apap_kp_rows")
@@ -718,14 +742,13 @@ class APAP:
         mesh_n, pt_size, _ = np.shape(vertices)
         if sample_n == 0:
             raise ValueError("local_homography needs at least one match")
-        cf1, cf2, tmats = self._condition(src_point, dst_point)
         torch, device = rt.torch_cuda(self.device)
         cells = mesh_n * pt_size
         anchors = scale_anchors(vertices, weight_scale(self.sigma))
-        points = np.empty((3, 1, sample_n, 2), dtype=np.float32)
-        points[0, 0], points[1, 0], points[2, 0] = cf1, cf2, src_point
+        points = np.empty((2, 1, sample_n, 2), dtype=np.float32)
+        points[0, 0], points[1, 0] = src_point, dst_point
         counts = np.array([sample_n], dtype=np.int32)
-        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors[None], tmats[None])
+        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors[None])
         h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, 1, cells)
         h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
         weight = LazyLocalWeight(np.asarray(src_point), np.asarray(vertices), self.gamma, self.sigma, self.device)
@@ -739,18 +762,15 @@ class APAP:
         verts = vertices if isinstance(vertices, (list, tuple)) else [vertices] * count
         mesh_n, pt_size, _ = np.shape(verts[0])
         cells = mesh_n * pt_size
-        prepared = [self._condition(s, d) for s, d in zip(src_points, dst_points)]
-        counts = np.array([cf1.shape[0] for cf1, _, _ in prepared], dtype=np.int32)
+        counts = np.array([np.shape(s)[0] for s in src_points], dtype=np.int32)
         if count == 0 or counts.min() == 0:
             raise ValueError("local_homography_batch needs at least one pair and one match per pair")
-        points = np.zeros((3, count, int(counts.max()), 2), dtype=np.float32)
-        for k, (cf1, cf2, _) in enumerate(prepared):
-            points[0, k, :counts[k]], points[1, k, :counts[k]] = cf1, cf2
-            points[2, k, :counts[k]] = src_points[k]
-        tmats = np.stack([m for _, _, m in prepared])
+        points = np.zeros((2, count, int(counts.max()), 2), dtype=np.float32)
+        for k, (s, d) in enumerate(zip(src_points, dst_points)):
+            points[0, k, :counts[k]], points[1, k, :counts[k]] = s, d
         anchors = np.stack([scale_anchors(v, weight_scale(self.sigma)) for v in verts])
         torch, device = rt.torch_cuda(self.device)
-        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors, tmats)
+        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors)
         h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, count, cells)
         h = rt.to_host(torch, h_dev).reshape(count, mesh_n, pt_size, 3, 3)
         return [h[k] for k in range(count)]

@@ -58,6 +58,125 @@ int launch_kp_rows(const float *cf1, const float *cf2, const float *src, const i
   return check_cuda(cudaGetLastError(), "k_kp_rows launch");
 }
 
+// ------------------------------------------------------------------------------------ k_condition
+// The O(N) prologue of local_homography (pyviz/apap.py:129-141) for one point set of one scene per CTA:
+// Hartley normaliser (centroid, mean distance -> t, pyviz/apap.py:35-59), the conditioner of the normalised points
+// (per-axis mean and unbiased standard deviation, pyviz/apap.py:63-89) and the conditioned points (pyviz/apap.py:92-100).
+// The reference reduces in float32 with numpy's pairwise order; here every reduction is float64 in a fixed order
+// (deterministic, and closer to the exact value), t and the conditioner are rounded to float32 like the reference's
+// arrays, and the per-point arithmetic is the reference's float32 arithmetic.  H is invariant to the normalisation in
+// exact arithmetic; the end-to-end difference against the host path is ~1e-6 of the 1e-4 gate (tests).
+// The public static methods of the Python class stay on the host, bit-exact with the reference.
+constexpr int kCondThreads = 512;
+
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();                                   // scratch may still be read from the previous sum
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double total = 0.0;
+  for (int w = 0; w < kCondThreads / 32; ++w) total += scratch[w];   // same order in every thread
+  return total;
+}
+
+// grid = (2, batch): blockIdx.x = 0 source points, 1 target points.  out_cond [2][batch][n_points][2] float32,
+// out_mats [batch][2][2][9] float32 = per scene and set {t (normaliser), conditioner}.
+__global__ void __launch_bounds__(kCondThreads) k_condition(const float2 *__restrict__ src, const float2 *__restrict__ dst,
+                                                            const int *__restrict__ counts, int n_points, int batch,
+                                                            float2 *__restrict__ out_cond, float *__restrict__ out_mats) {
+  __shared__ double scratch[kCondThreads / 32];
+  const int which = blockIdx.x, scene = blockIdx.y, tid = threadIdx.x;
+  const int n = counts ? min(counts[scene], n_points) : n_points;
+  const float2 *pts = (which ? dst : src) + (size_t)scene * n_points;
+  float2 *cond = out_cond + ((size_t)which * batch + scene) * n_points;
+  // centroid
+  double sx = 0.0, sy = 0.0;
+  for (int i = tid; i < n; i += kCondThreads) { const float2 p = pts[i]; sx += (double)p.x; sy += (double)p.y; }
+  const double cx = block_sum(sx, scratch) / (double)n, cy = block_sum(sy, scratch) / (double)n;
+  // mean distance to the centroid -> scale
+  double sd = 0.0;
+  for (int i = tid; i < n; i += kCondThreads) {
+    const float2 p = pts[i];
+    const double dx = (double)p.x - cx, dy = (double)p.y - cy;
+    sd += sqrt(dx * dx + dy * dy);
+  }
+  const double scale = 1.4142135623730951 / (block_sum(sd, scratch) / (double)n + 1e-8);
+  const float t00 = (float)scale, t02 = (float)(-scale * cx), t12 = (float)(-scale * cy);     // t is a float32 array
+  // normalised points nf = t [p; 1] (float32), their mean and variance per axis
+  double mx = 0.0, my = 0.0;
+  for (int i = tid; i < n; i += kCondThreads) {
+    const float2 p = pts[i];
+    const float nx = __fadd_rn(__fmul_rn(t00, p.x), t02), ny = __fadd_rn(__fmul_rn(t00, p.y), t12);
+    mx += (double)nx; my += (double)ny;
+  }
+  const double mux = block_sum(mx, scratch) / (double)n, muy = block_sum(my, scratch) / (double)n;
+  double vx = 0.0, vy = 0.0;
+  for (int i = tid; i < n; i += kCondThreads) {
+    const float2 p = pts[i];
+    const float nx = __fadd_rn(__fmul_rn(t00, p.x), t02), ny = __fadd_rn(__fmul_rn(t00, p.y), t12);
+    const double ex = (double)nx - mux, ey = (double)ny - muy;
+    vx += ex * ex; vy += ey * ey;
+  }
+  // unbiased standard deviation (std^2 * n / (n - 1), pyviz/apap.py:76-77), zero-deviation guard (:81-82)
+  double devx = sqrt(block_sum(vx, scratch) / (double)n * (double)n / (double)(n - 1));
+  double devy = sqrt(block_sum(vy, scratch) / (double)n * (double)n / (double)(n - 1));
+  devx = devx + (devx == 0.0 ? 1.0 : 0.0);
+  devy = devy + (devy == 0.0 ? 1.0 : 0.0);
+  const double kx = 1.4142135623730951 / devx, ky = 1.4142135623730951 / devy;
+  const float c00 = (float)kx, c02 = (float)(-kx * mux), c11 = (float)ky, c12 = (float)(-ky * muy);   // float32 array
+  // conditioned points: cf = nf * diag + translation, the reference's two float32 roundings (pyviz/apap.py:96-99)
+  for (int i = tid; i < n_points; i += kCondThreads) {
+    float2 o = make_float2(0.f, 0.f);
+    if (i < n) {
+      const float2 p = pts[i];
+      const float nx = __fadd_rn(__fmul_rn(t00, p.x), t02), ny = __fadd_rn(__fmul_rn(t00, p.y), t12);
+      o.x = __fadd_rn(__fmul_rn(nx, c00), c02);
+      o.y = __fadd_rn(__fmul_rn(ny, c11), c12);
+    }
+    cond[i] = o;
+  }
+  if (tid == 0) {
+    float *m = out_mats + ((size_t)scene * 2 + which) * 18;
+    const float t[9] = {t00, 0.f, t02, 0.f, t00, t12, 0.f, 0.f, 1.f};
+    const float c[9] = {c00, 0.f, c02, 0.f, c11, c12, 0.f, 0.f, 1.f};
+    for (int k = 0; k < 9; ++k) { m[k] = t[k]; m[9 + k] = c[k]; }
+  }
+}
+
+// T2inv = inv(N2) inv(C2), T1 = C1 N1 (pyviz/apap.py:165-166) from the float32 matrices of k_condition: the
+// inverses of these [[a, 0, b], [0, c, d], [0, 0, 1]] matrices in closed form, rounded to float32 like
+// np.linalg.inv of a float32 matrix, products in float64.  One thread per scene.
+__global__ void k_condition_mats(const float *__restrict__ mats, int batch, double *__restrict__ tmats) {
+  const int scene = blockIdx.x * blockDim.x + threadIdx.x;
+  if (scene >= batch) return;
+  const float *n1 = mats + (size_t)scene * 36, *c1 = n1 + 9, *n2 = n1 + 18, *c2 = n1 + 27;
+  auto inv = [](const float *a, double *o) {          // a = [[a0, 0, a2], [0, a4, a5], [0, 0, 1]]
+    const double i0 = 1.0 / (double)a[0], i4 = 1.0 / (double)a[4];
+    const double r[9] = {i0, 0.0, -(double)a[2] * i0, 0.0, i4, -(double)a[5] * i4, 0.0, 0.0, 1.0};
+    for (int k = 0; k < 9; ++k) o[k] = (double)(float)r[k];
+  };
+  auto mul = [](const double *a, const double *b, double *o) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+  };
+  double n2i[9], c2i[9], c1d[9], n1d[9];
+  inv(n2, n2i); inv(c2, c2i);
+  for (int k = 0; k < 9; ++k) { c1d[k] = (double)c1[k]; n1d[k] = (double)n1[k]; }
+  mul(n2i, c2i, tmats + (size_t)scene * 18);
+  mul(c1d, n1d, tmats + (size_t)scene * 18 + 9);
+}
+
+int launch_condition(const float *src, const float *dst, const int *counts, int batch, int n_points, float *cond,
+                     float *mats, double *tmats, cudaStream_t st) {
+  if (batch == 0 || n_points == 0) return 0;
+  k_condition<<<dim3(2, batch), kCondThreads, 0, st>>>(reinterpret_cast<const float2 *>(src), reinterpret_cast<const float2 *>(dst),
+                                                      counts, n_points, batch, reinterpret_cast<float2 *>(cond), mats);
+  k_condition_mats<<<(batch + 63) / 64, 64, 0, st>>>(mats, batch, tmats);
+  return check_cuda(cudaGetLastError(), "k_condition launch");
+}
+
 // ------------------------------------------------------------------------------------ k_kp_blocks
 // Block layout (include/apap_b200.h): per 8 keypoints the 8 x 64 tile [Ph | Pl] in the K-major
 // core-matrix layout -- element (k, column m) at float (k/4)*256 + (m/8)*32 + (m%8)*4 + k%4 -- then
@@ -352,6 +471,15 @@ int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_
   if (reinterpret_cast<uintptr_t>(kp_table) & 15u) return fail(APAP_E_ALIGN, "kp_rows: kp_table must be 16-byte aligned");
   return launch_kp_rows(src_cond, dst_cond, src_raw, counts, batch, n_points, n_kp_padded, scale, kp_table,
                         static_cast<cudaStream_t>(stream));
+}
+
+int apap_condition(const float *src, const float *dst, const int *counts, int batch, int n_points, float *cond,
+                   float *mats, double *tmats, void *stream) {
+  if (!src || !dst || !cond || !mats || !tmats) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || n_points <= 0 || batch > 65535) return fail(APAP_E_BADARG, "condition: bad sizes");
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(cond)) & 7u)
+    return fail(APAP_E_ALIGN, "condition: the point arrays must be 8-byte aligned");
+  return launch_condition(src, dst, counts, batch, n_points, cond, mats, tmats, static_cast<cudaStream_t>(stream));
 }
 
 int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_blocks, void *stream) {

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 16
+#define APAP_ABI_VERSION 17
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -221,6 +221,22 @@ int apap_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, vo
  *   grid, grid_inv : float [cells][9] (device);  flags : uint8 [cells] (device)
  */
 int apap_invert_grid(const float *grid, int cells, float *grid_inv, unsigned char *flags, void *stream);
+
+/*
+ * apap_condition: the O(N) prologue of APAP.local_homography on the device (pyviz/apap.py:129-141): Hartley
+ * normalisers (getNormalize2DPts, :35-59), conditioners (getConditionerFromPts, :63-89), conditioned points
+ * (point_normalize, :92-100) and the two de-normalisation matrices of :165-166, for `batch` scenes.  Reductions run
+ * in float64 in a fixed order; the matrices are rounded to float32 and the per-point arithmetic is float32, as in the
+ * reference.  (The Python class keeps the reference's static methods on the host, bit-exact; this entry point is what
+ * its local_homography uses, the results agree to ~1e-6 of the per-cell gate.)
+ *   src, dst : float [batch][n_points][2] raw matched points;  counts : int32 [batch] or NULL
+ *   cond     : out float [2][batch][n_points][2]: conditioned source points, conditioned target points
+ *              (= src_cond / dst_cond of apap_kp_rows); points past a scene's count are zero
+ *   mats     : out float [batch][2][2][9]: per scene {N1, C1, N2, C2} (normaliser and conditioner per set)
+ *   tmats    : out double [batch][18] = T2inv then T1 (the `tmats` of apap_eig_denorm)
+ */
+int apap_condition(const float *src, const float *dst, const int *counts, int batch, int n_points, float *cond,
+                   float *mats, double *tmats, void *stream);
 
 int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_raw, const int *counts, int batch,
                  int n_points, int n_kp_padded, double scale, float *kp_table, void *stream);

@@ -209,6 +209,36 @@ def test_gram_engines_agree_on_partial_sums():
     assert err.max() <= 2e-5
 
 
+@pytest.mark.parametrize("name,n_kp", [("mini", None), ("c1", None), ("c2", None), ("mini", 3), ("mini", 1)])
+def test_device_conditioning_agrees_with_the_reference_host_prologue(name, n_kp):
+    """apap_condition (float64 reductions in a fixed order) against the reference's numpy prologue, which the class
+    keeps on the host bit-exact (pyviz/apap.py:129-141): conditioned points and de-normalisation matrices to float32
+    accuracy, and the H grid of the public call against the one computed from the HOST prologue far inside the gate."""
+    import torch
+    sc = synth.make_scene(name) if n_kp is None else synth.make_scene(name, n_kp=n_kp)
+    st = _stitcher(sc)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    with np.errstate(all="ignore"):
+        cf1, cf2, tmats = st._condition(sc.src, sc.dst)
+    raw = torch.from_numpy(np.stack([sc.src, sc.dst])[:, None].astype(np.float32)).to(dev)
+    cond, tm = st.condition_device(raw)
+    cond, tm = cond.cpu().numpy(), tm.cpu().numpy()[0]
+    if sc.src.shape[0] == 1:                       # the reference divides by n - 1 = 0: NaN on both sides
+        assert not np.isfinite(tm).all() and not np.isfinite(tmats).all()
+        return
+    assert np.allclose(cond[0, 0], cf1, rtol=0, atol=2e-5) and np.allclose(cond[1, 0], cf2, rtol=0, atol=2e-5)
+    assert np.allclose(tm, tmats, rtol=2e-6, atol=1e-9 * np.abs(tmats).max())
+    if sc.src.shape[0] >= 8:
+        h_pub, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+        table, tmats_h = st._prepare(sc.src, sc.dst)                      # host prologue -> device K1 + K2
+        t_dev = st.kp_table_device(torch.from_numpy(table[None]).to(dev))
+        from cvx_proj_b200.apap import scale_anchors, weight_scale
+        a_dev = torch.from_numpy(scale_anchors(sc.vertices, weight_scale(sc.sigma))[None]).to(dev)
+        h_host = st.local_homography_device(t_dev, a_dev, torch.from_numpy(tmats_h[None]).to(dev), 1, sc.n_cells)
+        h_host = h_host.cpu().numpy().reshape(h_pub.shape)
+        assert _herr(h_pub, h_host, sc).max() <= 2e-5
+
+
 @pytest.mark.parametrize("n_kp", [5, 128, 1000, 2049])
 def test_device_kp_blocks_equal_host_restatement(n_kp):
     """apap_kp_blocks packs the tensor-core block table on the device: same bits as build_kp_blocks."""
