@@ -886,7 +886,11 @@ class APAP:
             flat[redo] = fixed
         return int(redo.size)
 
-    def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False):
+    def _warp(self, ori_img, local_homography, mesh, centre_img=None, force_exact=False, interpolation="nearest"):
+        if interpolation not in ("nearest", "bilinear"):
+            raise ValueError("interpolation must be 'nearest' (the reference's truncating lookup) or 'bilinear'")
+        if interpolation == "bilinear" and centre_img is not None:
+            raise ValueError("the fused warp + blend runs in the reference's nearest mode only")
         mesh_n, pt_size, _, _ = local_homography.shape
         ori_h, ori_w, _ = ori_img.shape
         on_device = not isinstance(ori_img, np.ndarray)
@@ -901,18 +905,41 @@ class APAP:
         self.invert_grid(local_homography, device)
         col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
         tables = self.warp_tables_device(local_homography, col_cell, row_cell, ori_w, ori_h, device)
-        out = self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)
+        if interpolation == "bilinear":
+            out = self.warp_bilinear_device(src_dev, tables, pt_size)
+        else:
+            out = self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)
         return out if on_device else rt.to_host(torch, out)
 
-    def local_warp(self, ori_img, local_homography, mesh, progress=False):
+    def warp_bilinear_device(self, src_dev, tables, grid_cols, out=None):
+        """Device-resident opt-in bilinear mode (``apap_warp_bilinear``): the canvas rows ``[tables.row0, tables.row1)``."""
+        torch, device = rt.torch_cuda(src_dev.device)
+        lib = rt.load_library()
+        fw = int(self.final_width)
+        if out is None:
+            out = torch.empty((tables.row1 - tables.row0, fw, 3), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_warp_bilinear(
+                src_dev.data_ptr(), src_dev.shape[0], src_dev.shape[1], tables.cell_hinv.data_ptr(),
+                tables.col_lut.data_ptr(), tables.row_blocks.data_ptr(), tables.n_blocks, grid_cols, fw,
+                int(self.offset_x), int(self.offset_y), tables.row0, tables.row1, out.data_ptr(), out.numel(),
+                rt.stream_ptr(torch, device)), "apap_warp_bilinear")
+        return out
+
+    def local_warp(self, ori_img, local_homography, mesh, progress=False, interpolation="nearest"):
         """Warp ``ori_img`` onto the canvas through the per-cell homographies (pyviz/apap.py:186-217).
 
         Like the reference it inverts ``local_homography`` IN PLACE (the caller's array holds the
         inverses afterwards).  ``mesh`` is the ``[2, mesh_n+1]`` edge array of ``get_mesh``.
         ``progress`` is accepted for compatibility (the reference's tqdm bar) and ignored.
         Returns the ``[final_height, final_width, 3]`` uint8 canvas, zero where nothing maps.
+
+        ``interpolation`` (extension): ``"nearest"`` is the reference's truncating lookup (pyviz/apap.py:214-215),
+        bit-exact; ``"bilinear"`` writes the same pixels (same float64 coordinates and strict bounds test) with a
+        bilinear sample at the mapped position (``cv.warpPerspective``'s convention, pyviz/utils.py:114), within
+        +-1 LSB of the float64 restatement ``oracle.apap_oracle.local_warp_bilinear``.
         """
-        return self._warp(ori_img, local_homography, mesh)
+        return self._warp(ori_img, local_homography, mesh, interpolation=interpolation)
 
     def local_warp_batch(self, ori_imgs, local_homographies, mesh, centre_imgs=None):
         """Extension (no reference API; its multi-image mode is a shell loop, run_all.sh:15,29): ``local_warp`` --

@@ -126,6 +126,26 @@ int apap_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, 
                      static_cast<cudaStream_t>(stream));
 }
 
+int apap_warp_bilinear(const uint8_t *src, int src_h, int src_w, const float *cell_hinv, const uint32_t *col_lut,
+                       const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x, int off_y, int row0,
+                       int row1, uint8_t *out_band, size_t out_band_bytes, void *stream) {
+  if (!src || !cell_hinv || !col_lut || !out_band || (n_blocks > 0 && !row_blocks)) return fail(APAP_E_BADARG, "null pointer");
+  if (n_blocks < 0 || src_h <= 0 || src_w <= 0 || canvas_w <= 0 || grid_cols <= 0 || row0 < 0 || row1 < row0)
+    return fail(APAP_E_BADARG, "bilinear warp: bad sizes");
+  if ((long long)src_w * src_h > 2147483647LL) return fail(APAP_E_TOOBIG, "bilinear warp: source image too large");
+  if (out_band_bytes < (size_t)(row1 - row0) * (size_t)canvas_w * 3)
+    return fail(APAP_E_BADARG, "bilinear warp: out_band is smaller than the rows [row0, row1) of the canvas");
+  if ((reinterpret_cast<uintptr_t>(col_lut) & 7u) || (reinterpret_cast<uintptr_t>(row_blocks) & 7u))
+    return fail(APAP_E_ALIGN, "bilinear warp: col_lut / row_blocks must be 8-byte aligned");
+  WarpParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = src; p.src_h = src_h; p.src_w = src_w; p.cell_hinv = cell_hinv;
+  p.col_lut = reinterpret_cast<const uint2 *>(col_lut); p.row_blocks = reinterpret_cast<const uint2 *>(row_blocks);
+  p.n_blocks = n_blocks; p.grid_cols = grid_cols; p.canvas_w = canvas_w; p.off_x = off_x; p.off_y = off_y;
+  p.row0 = row0; p.band_rows = row1 - row0; p.out = out_band;
+  return launch_warp_bilinear(p, static_cast<cudaStream_t>(stream));
+}
+
 int apap_warp_tiles_bytes(int canvas_w, int n_blocks, size_t *bytes) {
   if (!bytes || canvas_w <= 0 || n_blocks < 0) return fail(APAP_E_BADARG, "warp_tiles_bytes: bad arguments");
   *bytes = warp_tiles_bytes(canvas_w, n_blocks);

@@ -84,5 +84,6 @@ int launch_warp_tile(const WarpParams &w, bool words, const void *tiles, cudaStr
 int launch_warp_tiles(const WarpParams &w, const int *col_ext, void *tiles, size_t tiles_bytes, cudaStream_t st);
 bool warp_tile_usable(const WarpParams &w);
 size_t warp_tiles_bytes(int canvas_w, int n_blocks);
+int launch_warp_bilinear(const WarpParams &p, cudaStream_t st);
 
 }  // namespace apap

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 17
+#define APAP_ABI_VERSION 18
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -183,6 +183,17 @@ int apap_warp_tiles_bytes(int canvas_w, int n_blocks, size_t *bytes);
 int apap_warp_tiles(const float *cell_fast, const float *cell_hinv, const uint32_t *col_lut, const int *col_extent,
                     const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x, int off_y,
                     int src_h, int src_w, void *tiles, size_t tiles_bytes, void *stream);
+
+/*
+ * Opt-in bilinear mode of the mesh warp (no reference counterpart: APAP.local_warp truncates, pyviz/apap.py:214-215;
+ * BASELINE.json's north_star asks for a bilinear sample within +-1 LSB of a float64 restatement).  Same cell lookup,
+ * float64 coordinates and strict bounds test as the pixel loop of pyviz/apap.py:206-215 decide which pixels are
+ * written; the value is the bilinear sample at (tx, ty) with cv.warpPerspective's convention (pyviz/utils.py:114):
+ * x0 = floor(tx), fx = tx - x0, taps clamped to the image, rounded half up.  Tables as for apap_warp.
+ */
+int apap_warp_bilinear(const uint8_t *src, int src_h, int src_w, const float *cell_hinv, const uint32_t *col_lut,
+                       const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x, int off_y,
+                       int row0, int row1, uint8_t *out_band, size_t out_band_bytes, void *stream);
 
 /*
  * K4 -- uniform_blend (pyviz/apap_utils.py:75-88): out = both non-black ? (a + b) >> 1 : a + b,

@@ -289,6 +289,46 @@ def local_warp(ori_img, inv_h, mesh, final_wh, offset):
     return out
 
 
+def local_warp_bilinear(ori_img, inv_h, mesh, final_wh, offset):
+    """Float64 restatement of the OPT-IN bilinear mode of the mesh warp (no reference counterpart: the reference's
+    ``local_warp`` truncates, pyviz/apap.py:214-215; BASELINE.json's north_star asks for "bilinear sample ... within
+    +-1 LSB").  Everything up to the bounds test is ``local_warp`` above (pyviz/apap.py:196-213: cell lookup, float64
+    coordinates from the float32 inverted grid, strict ``0 < t < size``); the written pixels get the bilinear sample at
+    ``(tx, ty)`` with the convention of the reference's only bilinear sampler, ``cv.warpPerspective`` (pyviz/utils.py:114):
+    pixel centres at integer coordinates, taps ``floor`` and ``floor + 1`` clamped to the image, rounded half up."""
+    mesh_w, mesh_h = mesh
+    fw, fh = int(final_wh[0]), int(final_wh[1])
+    ox, oy = offset
+    oh, ow = ori_img.shape[0], ori_img.shape[1]
+    col = cell_lookup(mesh_w, fw)
+    row = cell_lookup(mesh_h, fh)
+    out = np.zeros((fh, fw, 3), dtype=np.uint8)
+    x = (np.arange(fw) - ox).astype(np.float64)
+    img = ori_img.astype(np.float64)
+    band = max(1, (1 << 21) // max(fw, 1))
+    for i0 in range(0, fh, band):
+        i1 = min(fh, i0 + band)
+        h = inv_h[row[i0:i1, None], col[None, :]].astype(np.float64)
+        y = (np.arange(i0, i1) - oy).astype(np.float64)[:, None]
+        xx = np.broadcast_to(x[None, :], (i1 - i0, fw))
+        t0 = h[..., 0, 0] * xx + h[..., 0, 1] * y + h[..., 0, 2]
+        t1 = h[..., 1, 0] * xx + h[..., 1, 1] * y + h[..., 1, 2]
+        t2 = h[..., 2, 0] * xx + h[..., 2, 1] * y + h[..., 2, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tx = t0 / t2
+            ty = t1 / t2
+        ok = (0 < tx) & (tx < ow) & (0 < ty) & (ty < oh)
+        tx, ty = tx[ok], ty[ok]
+        x0, y0 = np.floor(tx).astype(np.int64), np.floor(ty).astype(np.int64)
+        x1, y1 = np.minimum(x0 + 1, ow - 1), np.minimum(y0 + 1, oh - 1)
+        fx, fy = (tx - x0)[:, None], (ty - y0)[:, None]
+        val = ((1 - fx) * (1 - fy) * img[y0, x0] + fx * (1 - fy) * img[y0, x1] +
+               (1 - fx) * fy * img[y1, x0] + fx * fy * img[y1, x1])
+        blk = out[i0:i1]
+        blk[ok] = np.minimum(np.floor(val + 0.5), 255).astype(np.uint8)
+    return out
+
+
 def local_warp_loop(ori_img, inv_h, mesh, final_wh, offset):
     """pyviz/apap.py:206-215 pixel by pixel (pure Python; small canvases only)."""
     mesh_w, mesh_h = mesh

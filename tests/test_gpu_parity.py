@@ -864,3 +864,28 @@ def test_sharded_pass_over_nccl_two_gpus_is_bit_identical():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=repo)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "SHARDED NCCL CHECK PASSED" in res.stdout, res.stdout[-3000:]
+
+
+@pytest.mark.parametrize("name", ["mini", "c1", "c2"])
+def test_local_warp_bilinear_opt_in_within_one_lsb_of_float64_restatement(name):
+    """BASELINE.json north_star: "bilinear sample ... warped pixels within +-1 LSB".  The opt-in mode writes exactly the
+    pixels the reference's truncating mode writes and samples them bilinearly; gate: |GPU - float64 oracle| <= 1."""
+    sc = synth.make_scene(name)
+    img = sc.image(1)
+    st = _stitcher(sc)
+    h = orc.local_homography_gram64(sc.src, sc.dst, sc.vertices[::8, ::8], sc.gamma, sc.sigma) if name == "c2" else \
+        orc.local_homography_gram64(sc.src, sc.dst, sc.vertices, sc.gamma, sc.sigma)
+    if name == "c2":
+        h = np.repeat(np.repeat(h, 8, 0), 8, 1).copy()
+    inv = orc.invert_grid(h)
+    want = orc.local_warp_bilinear(img, inv, sc.mesh, (sc.final_w, sc.final_h), (sc.offset_x, sc.offset_y))
+    grid = h.copy()
+    got = st.local_warp(img, grid, sc.mesh, interpolation="bilinear")
+    assert np.array_equal(grid, inv)                                        # same in-place inverse as the parity mode
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1, f"max |diff| {diff.max()}"
+    assert (diff != 0).mean() < 0.02
+    nearest = st.local_warp(img, h.copy(), sc.mesh)
+    assert np.array_equal(got.any(axis=-1), nearest.any(axis=-1))           # the same pixels are written (images are >= 1)
+    with pytest.raises(ValueError):
+        st.local_warp(img, h.copy(), sc.mesh, interpolation="cubic")
