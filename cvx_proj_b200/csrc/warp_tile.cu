@@ -50,8 +50,14 @@ namespace apap {
 #ifndef APAP_TILE_CTAS
 #define APAP_TILE_CTAS 3
 #endif
+#ifndef APAP_TILE_STAGES
+#define APAP_TILE_STAGES 2       // source-box stages of the ring (3 stages x 24-row tiles measured the same: profiles/)
+#endif
+#ifndef APAP_TILE_BLOCKS
+#define APAP_TILE_BLOCKS 8       // row blocks per tile (8 -> 32 rows, 20 KB box; 6 -> 24 rows, 16 KB box)
+#endif
 #ifndef APAP_TILE_BOX_KB
-#define APAP_TILE_BOX_KB 20
+#define APAP_TILE_BOX_KB (APAP_TILE_BLOCKS == 8 ? 20 : 16)
 #endif
 #ifndef APAP_TILE_GROUP
 #define APAP_TILE_GROUP 4
@@ -60,9 +66,11 @@ constexpr int kWorkerWarps = 8;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kTileThreads = kWorkerThreads + 32;         // + the producer warp
 constexpr int kTileCols = 128;                            // 4 chunks of 32 columns
-constexpr int kTileBlocks = 8;                            // row blocks per tile
+constexpr int kStages = APAP_TILE_STAGES;
+constexpr int kTileBlocks = APAP_TILE_BLOCKS;             // row blocks per tile
 constexpr int kTileRows = kTileBlocks * kBlockRows;       // 32
 constexpr int kWarpRows = kTileRows / 2;                  // 16 canvas rows per worker warp
+static_assert(kTileBlocks <= 8 && kTileBlocks % 2 == 0 && kStages >= 2, "tile shape");
 constexpr int kWarpPitch = 32 * 3;                        // 96 B: a worker warp's 32 columns
 constexpr int kWarpOutBytes = kWarpRows * kWarpPitch;     // 1536 B: a warp's dense output block
 constexpr int kBoxBytes = APAP_TILE_BOX_KB * 1024;        // staged source box
@@ -74,7 +82,7 @@ constexpr int kCounterSlots = 64;                         // tile counters: laun
 constexpr int kGroupRows = APAP_TILE_GROUP;               // rows a lane processes per loop iteration (independent gathers in flight)
 static_assert(kGroupRows == 4 || kGroupRows == 8, "row group");
 constexpr int kRecRuns = 4;                               // cell rows of a tile whose records are staged ...
-constexpr int kRecCols = 16;                              // ... for at most this many cell columns (else global loads)
+constexpr int kRecCols = kStages > 2 ? 7 : 16;            // ... for at most this many cell columns (else global loads)
 
 enum TileMode : int { kBlack = 0, kStagedMode = 1, kGlobal = 3, kDone = 4 };
 
@@ -100,7 +108,7 @@ struct TileInfo {                // one tile, as k_tile_prep writes it and the w
   int c0;                        // first uint32 column of the box in the source's tensor map
   int ncc;                       // cell columns of the tile
   int pad;
-  int4 run[kTileBlocks];         // the tile's rows by cell row: {first canvas row, rows, cell row, dy of the first row}
+  int4 run[8];                   // the tile's rows by cell row: {first canvas row, rows, cell row, dy of the first row}
 };
 static_assert(sizeof(TileInfo) == 192, "TileInfo is copied as 12 uint4");
 
@@ -112,11 +120,11 @@ struct Stage {
 };
 
 struct TileSmem {
-  Stage st[2];
-  alignas(128) uint8_t out[2][kWorkerWarps][kWarpOutBytes];   // per stage, per worker warp: 16 rows x 96 B, dense
-  alignas(16) TileInfo info[2];
-  alignas(8) uint64_t full[2];
-  uint64_t empty[2];
+  Stage st[kStages];
+  alignas(128) uint8_t out[2][kWorkerWarps][kWarpOutBytes];   // double buffered, per worker warp: 16 rows x 96 B, dense
+  alignas(16) TileInfo info[kStages];
+  alignas(8) uint64_t full[kStages];
+  uint64_t empty[kStages];
 };
 
 static_assert(offsetof(Stage, zero) == kBoxBytes, "the zero word sits right behind the staged box");
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(256) k_tile_prep(const __grid_constant__ TileP
   const int r_first = __shfl_sync(0xffffffffu, i0, 0);
   const int r_last = __shfl_sync(0xffffffffu, i0 + n - 1, nbt - 1);
   TileInfo &f = tp.tiles[tile];
-  if (lane < kTileBlocks)
+  if (lane < 8)
     f.run[lane] = lane < n_runs ? make_int4(run_row0, run_row1 - run_row0 + 1, run_cr, run_dy) : make_int4(0, 0, 0, 0);
   if (lane == 0) {
     f.x_lo = x_lo; f.y_lo = y_lo; f.pitch = bpitch; f.shift = shift; f.mode = mode;
@@ -468,11 +476,10 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    mbar_init(&sm.full[0], 1); mbar_init(&sm.full[1], 1);
-    mbar_init(&sm.empty[0], kWorkerWarps); mbar_init(&sm.empty[1], kWorkerWarps);
+    for (int q = 0; q < kStages; ++q) { mbar_init(&sm.full[q], 1); mbar_init(&sm.empty[q], kWorkerWarps); }
     mbar_fence_init();
   }
-  if (tid < 8) reinterpret_cast<uint32_t *>(sm.st[tid >> 2].zero)[tid & 3] = 0u;
+  if (tid < 4 * kStages) reinterpret_cast<uint32_t *>(sm.st[tid >> 2].zero)[tid & 3] = 0u;
   __syncthreads();
 
   if (warp == kWorkerWarps) {
@@ -502,10 +509,11 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
     };
     fetch(tile);
     for (int k = 0;; ++k) {
-      const int s = k & 1;
+      const int s = k % kStages;
+      const uint32_t ring_par = (uint32_t)(k / kStages) & 1u;
       TileInfo &f = sm.info[s];
       if (tile >= tp.n_tiles) {                            // no tiles left: tell the workers, release the counter slot
-        mbar_wait(&sm.empty[s], ((k >> 1) & 1) ^ 1);
+        mbar_wait(&sm.empty[s], ring_par ^ 1u);
         if (lane == 0) {
           f.mode = kDone;
           mbar_arrive(&sm.full[s]);
@@ -525,19 +533,21 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
       const int bpitch = __shfl_sync(0xffffffffu, (int)rec.z, 0);
       const int mode = __shfl_sync(0xffffffffu, (int)rec.x, 1);          // uint4 #1 = {mode, r_first, n_rows, c_lo}
       const int c_lo = __shfl_sync(0xffffffffu, (int)rec.w, 1);
-      const int rec_ok = __shfl_sync(0xffffffffu, (int)rec.x, 2);        // uint4 #2 = {rec_ok, n_runs, j0, jw}
+      int rec_ok = __shfl_sync(0xffffffffu, (int)rec.x, 2);              // uint4 #2 = {rec_ok, n_runs, j0, jw}
+      if (tp.lab & 8) rec_ok = 0;                                        // LAB: no record staging (workers load from global)
       const int n_runs = __shfl_sync(0xffffffffu, (int)rec.y, 2);
       const int shape = __shfl_sync(0xffffffffu, (int)rec.x, 3);         // uint4 #3 = {shape, c0, ncc, pad}
       const int c0 = __shfl_sync(0xffffffffu, (int)rec.y, 3);
       const int ncc = __shfl_sync(0xffffffffu, (int)rec.z, 3);
-      const int run_cr = __shfl_sync(0xffffffffu, (int)rec.z, 4 + min(lane, kTileBlocks - 1));   // uint4 #4+r = run r
+      const int run_cr = __shfl_sync(0xffffffffu, (int)rec.z, 4 + min(lane, 7));   // uint4 #4+r = run r
       uint2 cur_lut[kTileCols / 32];
 #pragma unroll
       for (int q = 0; q < kTileCols / 32; ++q) cur_lut[q] = lut[q];
       fetch(tile_next);                                      // in flight while this tile is published
 
-      mbar_wait(&sm.empty[s], ((k >> 1) & 1) ^ 1);           // the workers have left this stage
+      mbar_wait(&sm.empty[s], ring_par ^ 1u);                // the workers have left this stage
       if (lane < 12) reinterpret_cast<uint4 *>(&f)[lane] = cur;
+      if ((tp.lab & 8) && lane == 0) f.rec_ok = 0;
 #pragma unroll
       for (int q = 0; q < kTileCols / 32; ++q) sm.st[s].lut[lane + 32 * q] = cur_lut[q];
       __syncwarp();
@@ -580,10 +590,10 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
   const int lane_col = cw * 32 + lane;
   const uint32_t pitch = (uint32_t)p.canvas_w * 3u;
   for (int k = 0;; ++k) {
-    const int s = k & 1;
-    uint8_t *warp_out = sm.out[s][warp];
-    if (tp.store_mode == 2) bulk_wait_read_but_one();        // this thread's store of two tiles ago has read out[s]
-    mbar_wait_relaxed(&sm.full[s], (k >> 1) & 1);            // box, records, LUT and info of this tile have landed
+    const int s = k % kStages;
+    uint8_t *warp_out = sm.out[k & 1][warp];
+    if (tp.store_mode == 2) bulk_wait_read_but_one();        // this thread's store of two tiles ago has read its block
+    mbar_wait_relaxed(&sm.full[s], (uint32_t)(k / kStages) & 1u);   // box, records, LUT and info of this tile have landed
     const TileInfo &f = sm.info[s];
     const int mode = f.mode;
     if (mode == kDone) break;
@@ -635,7 +645,7 @@ __global__ void __launch_bounds__(kTileThreads, APAP_TILE_CTAS) k_warp_tile(cons
       // all workers together: whole rows of the tile out of the eight blocks (tile row r < 16: first warps' blocks,
       // row r; else the second warps' blocks, row r - second0)
       worker_barrier();
-      const uint8_t *blocks = sm.out[s][0];
+      const uint8_t *blocks = sm.out[k & 1][0];
       const int second0 = n_rows >= kWarpRows ? n_rows - kWarpRows : kWarpRows;
       const uint32_t row_bytes = (uint32_t)jw * 3u;
       uint8_t *gout = p.out + ((size_t)(r_first - p.row0) * pitch + (size_t)j0 * 3);

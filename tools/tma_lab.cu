@@ -64,6 +64,56 @@ __global__ void k_lat(const __grid_constant__ CUtensorMap m, int bytes, int c0, 
   }
 }
 
+// The tile engine's load pattern: every CTA keeps two box loads in flight (ring of two stages) over never-touched
+// addresses (cold) or a small set (warm), optionally with 8 small tensor stores per box like the engine's output.
+__global__ void k_ring(const __grid_constant__ CUtensorMap m, const __grid_constant__ CUtensorMap om, int bytes, int tiles_x,
+                       int n_tiles, int warm, int stores, long long *out) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 2 * 20480 + 12288);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar + 1)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    long long sum = 0, cnt = 0, worst = 0;
+    unsigned long long t_issue[2];
+    auto issue = [&](int k, int tile) {
+      const int s = k & 1;
+      const int t = warm ? (tile % 64) : tile;
+      const int c0 = (t % tiles_x) * 96, c1 = (t / tiles_x) * 31;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_issue[s]));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar + s)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(sm + s * 20480)),
+                   "l"(reinterpret_cast<uint64_t>(&m)), "r"(c0), "r"(c1), "r"(s32(bar + s))
+                   : "memory");
+    };
+    int tile = blockIdx.x, k = 0;
+    issue(0, tile);
+    if (tile + (int)gridDim.x < n_tiles) issue(1, tile + gridDim.x);
+    for (; tile < n_tiles; tile += gridDim.x, ++k) {
+      const int s = k & 1;
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(s32(bar + s)), "r"((k >> 1) & 1) : "memory");
+      }
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      const long long d = (long long)(t1 - t_issue[s]);
+      sum += d; ++cnt; worst = d > worst ? d : worst;
+      if (stores) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int w = 0; w < 8; ++w)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&om)),
+                       "r"(s32(sm + 2 * 20480 + w * 1536)), "r"((tile % tiles_x) * 96 + (w & 3) * 24), "r"((tile / tiles_x) * 32 + (w >> 2) * 16)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+      if (tile + 2 * (int)gridDim.x < n_tiles) issue(k + 2, tile + 2 * gridDim.x);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    out[3 * blockIdx.x] = sum / (cnt ? cnt : 1); out[3 * blockIdx.x + 1] = worst; out[3 * blockIdx.x + 2] = cnt;
+  }
+}
+
 typedef CUresult (*Enc)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -87,6 +137,42 @@ int main(int argc, char **argv) {
       {"u8 box 256x40 c0=48", CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 40, 48, 40},
       {"u8 box 256x40 c0=33", CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, 256, 40, 33, 40},
   };
+  if (argc > 1 && atoi(argv[1]) == 98) {                     // the tile engine's ring of box loads, cold / warm, with / without stores
+    const int W2 = 7680, H2 = 4320, pitch2 = W2 * 3, CW = 8896, CH = 4664, cpitch = CW * 3;
+    uint8_t *d2, *o2; cudaMalloc(&d2, (size_t)pitch2 * H2); cudaMemset(d2, 7, (size_t)pitch2 * H2);
+    cudaMalloc(&o2, (size_t)cpitch * CH);
+    uint8_t *flush; cudaMalloc(&flush, 256u << 20);
+    long long *lo; cudaMalloc(&lo, 8 * 3 * 1024);
+    auto mk = [&](CUtensorMap *m, void *base, int pitch, int rows, int bw, int bh) {
+      const cuuint64_t dims[2] = {(cuuint64_t)(pitch / 4), (cuuint64_t)rows};
+      const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+      const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+      const cuuint32_t ones[2] = {1, 1};
+      return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUtensorMap m, om;
+    mk(&m, d2, pitch2, H2, 128, 40); mk(&om, o2, cpitch, CH, 24, 16);
+    const int tiles_x = 60, n_tiles = 60 * 139;               // 96 u32 = 128 px per tile across, 31 rows down: the whole image once
+    cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
+    for (int warm = 0; warm < 2; ++warm)
+      for (int stores = 0; stores < 2; ++stores) {
+        cudaMemset(flush, warm + stores, 256u << 20);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        k_ring<<<444, 32, 60000>>>(m, om, 20480, tiles_x, n_tiles, warm, stores, lo);
+        cudaEventRecord(e1);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        long long h[3 * 444]; cudaMemcpy(h, lo, sizeof(h), cudaMemcpyDeviceToHost);
+        long long mean = 0, worst = 0;
+        for (int i = 0; i < 444; ++i) { mean += h[3 * i]; worst = h[3 * i + 1] > worst ? h[3 * i + 1] : worst; }
+        printf("ring: %s boxes, %s: %s kernel %.1f us, issue->landed mean %lld ns, worst %lld ns (%d tiles, 444 CTAs x 2 in flight)\n",
+               warm ? "warm (64 positions)" : "cold (whole 8K image once)", stores ? "with 8 stores per box" : "loads only",
+               cudaGetErrorName(e2), ms * 1e3, mean / 444, worst, n_tiles);
+      }
+    return 0;
+  }
   if (argc > 1 && atoi(argv[1]) == 99) {                     // latency of box loads, alone and with every SM loading
     const int W2 = 7680, H2 = 4320, pitch2 = W2 * 3;
     uint8_t *d2; cudaMalloc(&d2, (size_t)pitch2 * H2); cudaMemset(d2, 7, (size_t)pitch2 * H2);
