@@ -19,7 +19,7 @@ KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
 WARP_BLOCK_ROWS = 4
-ABI_VERSION = 18
+ABI_VERSION = 19
 KP_BLOCK = 8
 KP_BLOCK_FLOATS = 528
 GRAM_TCGEN05 = 0
@@ -28,6 +28,7 @@ EIG_AUTO = 0
 EIG_JACOBI = 1
 WARP_FORCE_EXACT = 1
 WARP_LEGACY = 2
+WARP_TILE_FUSED = 4
 
 # symbol -> (restype, argtypes); tests check every symbol of include/apap_b200.h is exported
 SIGNATURES = {

@@ -405,8 +405,9 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
   if (multicast && (!words || canvas_w % 16 != 0 || (reinterpret_cast<uintptr_t>(out_band) & 15u)))
     return fail(APAP_E_ALIGN, "warp: multicast stores need canvas_w % 16 == 0 and a 16-byte aligned band");
   // the tile engine (csrc/warp_tile.cu) when the caller built tile records and the source rows are 16-byte aligned
-  // (plain warp only: fused with the blend, the strip kernel's batched centre loads are faster -- c2 49 us against 75 us)
-  if (tiles && !centre && !(flags & APAP_WARP_LEGACY) && warp_tile_usable(p)) {
+  // (plain warp by default: fused with the blend, the strip kernel's batched centre loads are faster -- c2 49 us against
+  // 65 us, c3 169 against 198 --; APAP_WARP_TILE_FUSED asks for the tile engine's fused variant all the same, for the A/B)
+  if (tiles && (!centre || (flags & APAP_WARP_TILE_FUSED)) && !(flags & APAP_WARP_LEGACY) && warp_tile_usable(p)) {
     if (reinterpret_cast<uintptr_t>(tiles) & 15u) return fail(APAP_E_ALIGN, "warp: tiles must be 16-byte aligned");
     return launch_warp_tile(p, words, tiles, st);
   }

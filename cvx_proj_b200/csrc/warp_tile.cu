@@ -241,6 +241,11 @@ __device__ __forceinline__ void tile_rows(const WarpParams &p, const CellState &
       so[2 * k + e] = clear ? off : guard;
     }
   }
+  uint32_t cv[kBlend ? kRows : 1];              // fused blend: the centre image's pixels, all loads in flight before the gathers
+  if (kBlend) {
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) cv[k] = centre_px(p, x, y + k, col_ok);
+  }
   bool any_guard = false;
 #pragma unroll
   for (int k = 0; k < kRows; ++k) {
@@ -259,7 +264,7 @@ __device__ __forceinline__ void tile_rows(const WarpParams &p, const CellState &
       }
     }
     if (kBlend) {
-      const uint32_t val = blend_px(b0 | (b1 << 8) | (b2 << 16), centre_px(p, x, y + k, col_ok));
+      const uint32_t val = blend_px(b0 | (b1 << 8) | (b2 << 16), cv[k]);
       b0 = val & 0xffu; b1 = (val >> 8) & 0xffu; b2 = val >> 16;
     }
     uint8_t *dst = orow + k * kWarpPitch;
@@ -277,7 +282,7 @@ __device__ __forceinline__ void tile_rows(const WarpParams &p, const CellState &
         const uint8_t *q = p.src + (size_t)(unsigned)idx * 3;
         val = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
       }
-      if (kBlend) val = blend_px(val, centre_px(p, x, y + k, col_ok));
+      if (kBlend) val = blend_px(val, cv[k]);
       uint8_t *dst = orow + k * kWarpPitch;
       dst[0] = (uint8_t)val; dst[1] = (uint8_t)(val >> 8); dst[2] = (uint8_t)(val >> 16);
     }

@@ -12,7 +12,7 @@ p = bench.Pass(torch, dev, name)
 p.gram(); p.eig(); p.prepare_warp()
 flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
 def call(legacy, fused):
-    p.st.warp_device(p.img, p.tables, p.sc.mesh_cells, out=p.canvas, legacy=legacy,
+    p.st.warp_device(p.img, p.tables, p.sc.mesh_cells, out=p.canvas, legacy=legacy, tile_fused=fused,
                      centre_dev=p.centre if fused else None)
 def run(legacy, fused, warm, reps=20):
     ts = []
