@@ -182,6 +182,16 @@ int apap_multicast_copy(const void *src, void *multicast_dst, size_t bytes, void
   return launch_multicast_copy(src, multicast_dst, bytes, static_cast<cudaStream_t>(stream));
 }
 
+int apap_peer_copy(const void *src, void *const *peer_dsts, int n_peers, size_t bytes, void *stream) {
+  if (!src || (!peer_dsts && n_peers)) return fail(APAP_E_BADARG, "peer_copy: null pointer");
+  if (n_peers < 0 || n_peers > APAP_MAX_PEERS) return fail(APAP_E_BADARG, "peer_copy: 0 <= n_peers <= APAP_MAX_PEERS");
+  if ((bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u)) return fail(APAP_E_ALIGN, "peer_copy: size and addresses must be multiples of 16 bytes");
+  for (int k = 0; k < n_peers; ++k)
+    if (!peer_dsts[k] || (reinterpret_cast<uintptr_t>(peer_dsts[k]) & 15u))
+      return fail(APAP_E_ALIGN, "peer_copy: peer addresses must be non-null multiples of 16 bytes");
+  return launch_peer_copy(src, peer_dsts, n_peers, bytes, static_cast<cudaStream_t>(stream));
+}
+
 int apap_pipe_probe(int kind, int iters, float *sink, double *ops, void *stream) {
   if (!sink || iters <= 0) return fail(APAP_E_BADARG, "probe: bad arguments");
   return launch_probe(kind, iters, sink, ops, static_cast<cudaStream_t>(stream));

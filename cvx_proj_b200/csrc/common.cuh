@@ -59,6 +59,7 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
 int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, cudaStream_t st);
 int launch_probe(int kind, int iters, float *sink, double *ops, cudaStream_t st);
 int launch_multicast_copy(const void *src, void *mc_dst, size_t bytes, cudaStream_t st);
+int launch_peer_copy(const void *src, void *const *peers, int n_peers, size_t bytes, cudaStream_t st);
 
 // ---- small PTX helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

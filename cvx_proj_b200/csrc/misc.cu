@@ -86,6 +86,43 @@ int launch_multicast_copy(const void *src, void *mc_dst, size_t bytes, cudaStrea
   return check_cuda(cudaGetLastError(), "k_multicast_copy launch");
 }
 
+// The same broadcast by unicast stores: each 16 bytes of the local band are written into every listed peer's buffer
+// (peer-mapped device addresses, e.g. torch symmetric memory's buffer_ptrs + offset).  A rank sends its band once per
+// peer, but no GPU receives its own band back from the switch, as it does through a multicast mapping that includes
+// it: (N-1)/N of the panorama comes in per GPU instead of all of it.
+struct PeerList {
+  uint4 *dst[APAP_MAX_PEERS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) k_peer_copy(const uint4 *__restrict__ src, PeerList pl, size_t n_vec) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += 2 * stride) {
+    const bool two = i + stride < n_vec;
+    const uint4 a = __ldcs(src + i);
+    uint4 b = a;
+    if (two) b = __ldcs(src + i + stride);
+    for (int k = 0; k < pl.n; ++k) {
+      pl.dst[k][i] = a;
+      if (two) pl.dst[k][i + stride] = b;
+    }
+  }
+}
+
+int launch_peer_copy(const void *src, void *const *peers, int n_peers, size_t bytes, cudaStream_t st) {
+  if (bytes == 0 || n_peers == 0) return 0;
+  PeerList pl;
+  pl.n = n_peers;
+  for (int k = 0; k < n_peers; ++k) pl.dst[k] = reinterpret_cast<uint4 *>(peers[k]);
+  const size_t n_vec = bytes / 16;
+  size_t blocks = (n_vec + 511) / 512;
+  const size_t cap = (size_t)sm_count_cached() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_peer_copy<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(src), pl, n_vec);
+  return check_cuda(cudaGetLastError(), "k_peer_copy launch");
+}
+
 int launch_probe(int kind, int iters, float *sink, double *ops, cudaStream_t st) {
   const int blocks = sm_count_cached() * 8;
   if (kind == APAP_PROBE_FFMA) {

@@ -300,6 +300,16 @@ int apap_power_iterate(const double *m, int n, double *y, double *norms, int fir
 int apap_multicast_copy(const void *src, void *multicast_dst, size_t bytes, void *stream);
 
 /*
+ * The same assembly by unicast stores: `bytes` at `src` are written to each of the `n_peers` device addresses in the
+ * HOST array `peer_dsts` (the band's address inside every OTHER GPU's panorama: peer-mapped pointers, e.g. torch
+ * symmetric memory's buffer_ptrs[r] + offset).  The rank sends its band n_peers times, but no GPU receives its own band
+ * back from the switch as it does through a multicast mapping that includes the sender.  Size and all addresses
+ * multiples of 16; the caller synchronises the group.
+ */
+#define APAP_MAX_PEERS 15
+int apap_peer_copy(const void *src, void *const *peer_dsts, int n_peers, size_t bytes, void *stream);
+
+/*
  * Pipe probes for the roofline denominators that MEASURED_PEAKS.json does not hold.  Runs `iters` x 16
  * independent operations per thread on every SM and returns the operation count in `ops`; the caller
  * times the launch with events.
