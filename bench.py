@@ -308,6 +308,7 @@ class Pass:
         self.table = self.st.kp_table_device(self.rows)[0]                   # the engine's table (blocks for tcgen05)
         self.anchors = torch.from_numpy(scale_anchors(verts, weight_scale(sc.sigma))).to(device)
         self.tmats = torch.from_numpy(tmats).to(device)
+        self.t_bound = self.st.weight_bound_device(self.points[2], None, self.anchors[None])   # as the public call does
         self.k_splits, self.cells_padded, nbytes = rt.gram_plan(self.cells, self.n_pad, self.engine)
         self.partials = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
         self.h_out = torch.empty((self.cells, 9), dtype=torch.float32, device=device)
@@ -318,14 +319,14 @@ class Pass:
     # -- moving DLT
     def gram(self):
         self.rt.check(self.lib.apap_gram_partials(self.table.data_ptr(), self.anchors.data_ptr(), 1, self.cells,
-                                                  self.n_pad, self.g2, self.engine, self.partials.data_ptr(),
-                                                  self.stream), "gram")
+                                                  self.n_pad, self.g2, self.engine, self.t_bound.data_ptr(),
+                                                  self.partials.data_ptr(), self.stream), "gram")
 
     def dlt(self, overlap=True):
         """K1 + K2 as the public call launches them (K2 a programmatic dependent of K1 when ``overlap``)."""
         self.st.local_homography_device(self.table[None], self.anchors[None], self.tmats[None], 1, self.cells,
                                         out_h=self.h_out[None] if self.h_out.dim() == 2 else self.h_out,
-                                        partials=self.partials, overlap=overlap)
+                                        partials=self.partials, overlap=overlap, t_bound=self.t_bound)
 
     def eig(self):
         self.rt.check(self.lib.apap_eig_denorm(self.partials.data_ptr(), self.tmats.data_ptr(), 1, self.cells,
@@ -793,9 +794,13 @@ def run_c4_c5(torch, device, flush, mufu_peak):
         out_h = torch.empty((1, cells, 9), dtype=torch.float32, device=device)
         lib, stream = rt.load_library(), rt.stream_ptr(torch, device)
         g2 = float(np.float32(sc.gamma ** 2))
+        bound = st.weight_bound_device(torch.from_numpy(np.ascontiguousarray(sc.src[None], dtype=np.float32)).to(device),
+                                       None, a_dev)
         ms_gram = timed(lambda: rt.check(lib.apap_gram_partials(t_dev.data_ptr(), a_dev.data_ptr(), 1, cells, n_pad, g2,
-                                                                rt.GRAM_TCGEN05, partials.data_ptr(), stream)))
-        ms_both = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, 1, cells, out_h=out_h, partials=partials))
+                                                                rt.GRAM_TCGEN05, bound.data_ptr(), partials.data_ptr(),
+                                                                stream)))
+        ms_both = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, 1, cells, out_h=out_h, partials=partials,
+                                                           t_bound=bound))
         launches += 8 * 3
         sweep.append({"n_kp": n_kp, "cells": cells, "k_splits": ks, "gram_ms": ms_gram, "k1_k2_ms": ms_both,
                       "cells_per_s": cells / (ms_both * 1e-3), "xu_frac": 2.0 * cells * n_pad / (ms_gram * 1e-3) / mufu_peak})
@@ -811,7 +816,10 @@ def run_c4_c5(torch, device, flush, mufu_peak):
     _, _, nbytes = rt.gram_plan(cells, n_pad, rt.GRAM_TCGEN05)
     partials = torch.empty(pairs * nbytes // 4, dtype=torch.float32, device=device)
     out_h = torch.empty((pairs, cells, 9), dtype=torch.float32, device=device)
-    ms_batch = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, pairs, cells, out_h=out_h, partials=partials))
+    raw = np.stack([np.ascontiguousarray(sc.src, dtype=np.float32) for sc in scs])      # c4 scenes have equal match counts
+    bound = st.weight_bound_device(torch.from_numpy(raw).to(device), None, a_dev)
+    ms_batch = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, pairs, cells, out_h=out_h, partials=partials,
+                                                        t_bound=bound))
     launches += 8 * 2
     c4 = {"workload": _workload_desc("c4") + f", batch of {pairs} pairs in one launch", "batch_ms": ms_batch,
           "cells_per_s": pairs * cells / (ms_batch * 1e-3),

@@ -629,7 +629,7 @@ class APAP:
         Layout: float32 points [2, b, n, 2] (raw source, raw target) | int32 counts [b] | float32 anchors [b, cells, 2]
         (every section starts 16-byte aligned).  The O(N) prologue of pyviz/apap.py:129-141 then runs on the device
         (``apap_condition``).  Returns the keypoint ROW table built from the points on the device, the anchors, the
-        de-normalisation matrices."""
+        de-normalisation matrices, the per-scene weight bound (``weight_bound_device``)."""
         if not hasattr(self, "_stage"):
             self._stage = _PinnedStage()
         p_u8, c_u8, a_u8 = self._stage.upload(torch, device, (points, counts, anchors))
@@ -637,7 +637,23 @@ class APAP:
         counts_dev = c_u8.view(torch.int32)
         cond, tmats = self.condition_device(raw, counts_dev)
         rows = self.kp_rows_device((cond[0], cond[1], raw[0]), counts_dev)
-        return rows, a_u8.view(torch.float32).view(anchors.shape), tmats
+        anchors_dev = a_u8.view(torch.float32).view(anchors.shape)
+        return rows, anchors_dev, tmats, self.weight_bound_device(raw[0], counts_dev, anchors_dev)
+
+    def weight_bound_device(self, raw_src_dev, counts_dev, anchors_dev):
+        """``apap_weight_bound``: per scene an upper bound of the pre-scaled distance of pyviz/apap.py:150-151 over all
+        (cell, match) pairs -- K1 leaves the clamp of :152 out for a scene where it cannot trigger (same bits).
+        ``raw_src_dev`` float32 ``[batch, n, 2]``, ``anchors_dev`` float32 ``[batch, cells, 2]`` (pre-scaled)."""
+        torch, device = rt.torch_cuda(raw_src_dev.device)
+        lib = rt.load_library()
+        batch, n, _ = raw_src_dev.shape
+        bound = torch.empty(batch, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rt.check(lib.apap_weight_bound(raw_src_dev.data_ptr(), counts_dev.data_ptr() if counts_dev is not None else None,
+                                           batch, n, weight_scale(self.sigma), anchors_dev.data_ptr(),
+                                           int(anchors_dev.shape[1]), bound.data_ptr(), rt.stream_ptr(torch, device)),
+                     "apap_weight_bound")
+        return bound
 
     def condition_device(self, raw_dev, counts_dev=None):
         """``apap_condition``: the normalisers, conditioners and conditioned points of pyviz/apap.py:129-141 on the device.
@@ -701,12 +717,13 @@ class APAP:
         return hit[1]
 
     def local_homography_device(self, table_dev, anchors_dev, tmats_dev, batch, cells, out_h=None, partials=None,
-                                sweeps=None, solver=rt.EIG_AUTO, overlap=True):
+                                sweeps=None, solver=rt.EIG_AUTO, overlap=True, t_bound=None):
         """Device-resident K1 + K2 (no host traffic): tensors in, ``[batch, cells, 9]`` float32 out.
         ``table_dev`` / ``anchors_dev`` hold pre-scaled coordinates (``build_kp_table`` or, for the
         tensor-core engine, ``build_kp_blocks``; ``scale_anchors``); the engine follows from the table's shape.
         ``overlap``: launch K2 as a programmatic dependent of K1 (it starts on finished cell tiles while K1's last
-        CTAs are still running); same results either way."""
+        CTAs are still running); same results either way.  ``t_bound``: float32 ``[batch]`` from ``weight_bound_device``
+        (K1 skips the clamp where it cannot trigger; same results)."""
         torch, device = rt.torch_cuda(table_dev.device)
         lib = rt.load_library()
         engine = rt.GRAM_TCGEN05 if table_dev.shape[-1] == KP_BLOCK_FLOATS else rt.GRAM_FFMA2
@@ -722,7 +739,8 @@ class APAP:
             with torch.cuda.device(device):
                 rt.check(lib.apap_local_homography(
                     table_dev.data_ptr(), anchors_dev.data_ptr(), tmats_dev.data_ptr(), batch, cells, n_pad,
-                    float(np.float32(float(self.gamma) ** 2)), engine, int(solver), partials.data_ptr(),
+                    float(np.float32(float(self.gamma) ** 2)), engine, int(solver),
+                    t_bound.data_ptr() if t_bound is not None else None, partials.data_ptr(),
                     counters.data_ptr() if counters is not None else None, out_h.data_ptr(),
                     sweeps.data_ptr() if sweeps is not None else None, rt.stream_ptr(torch, device)),
                     "apap_local_homography")
@@ -748,8 +766,8 @@ class APAP:
         points = np.empty((2, 1, sample_n, 2), dtype=np.float32)
         points[0, 0], points[1, 0] = src_point, dst_point
         counts = np.array([sample_n], dtype=np.int32)
-        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors[None])
-        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, 1, cells)
+        t_dev, a_dev, m_dev, bound = self._upload_scene(torch, device, points, counts, anchors[None])
+        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, 1, cells, t_bound=bound)
         h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
         weight = LazyLocalWeight(np.asarray(src_point), np.asarray(vertices), self.gamma, self.sigma, self.device)
         return h, weight
@@ -770,8 +788,8 @@ class APAP:
             points[0, k, :counts[k]], points[1, k, :counts[k]] = s, d
         anchors = np.stack([scale_anchors(v, weight_scale(self.sigma)) for v in verts])
         torch, device = rt.torch_cuda(self.device)
-        t_dev, a_dev, m_dev = self._upload_scene(torch, device, points, counts, anchors)
-        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, count, cells)
+        t_dev, a_dev, m_dev, bound = self._upload_scene(torch, device, points, counts, anchors)
+        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, count, cells, t_bound=bound)
         h = rt.to_host(torch, h_dev).reshape(count, mesh_n, pt_size, 3, 3)
         return [h[k] for k in range(count)]
 

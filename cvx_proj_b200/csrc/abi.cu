@@ -61,12 +61,12 @@ int apap_gram_plan(int cells, int n_kp_padded, int engine, int *k_splits, int *c
 }
 
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
-                       float gamma_sq, int engine, float *partials, void *stream) {
+                       float gamma_sq, int engine, const float *t_bound, float *partials, void *stream) {
   int rc = check_table(kp_table, anchors, batch, cells, n_kp_padded);
   if (rc) return rc;
   if (!partials) return fail(APAP_E_BADARG, "null partials");
   if (engine == APAP_GRAM_TCGEN05)
-    return launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials, nullptr,
+    return launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, t_bound, partials, nullptr,
                           static_cast<cudaStream_t>(stream));
   if (engine != APAP_GRAM_FFMA2) return fail(APAP_E_BADARG, "gram: unknown engine");
   return launch_gram(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials,
@@ -83,10 +83,10 @@ int apap_eig_denorm(const float *partials, const double *tmats, int batch, int c
 }
 
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats, int batch, int cells,
-                          int n_kp_padded, float gamma_sq, int engine, int solver,
+                          int n_kp_padded, float gamma_sq, int engine, int solver, const float *t_bound,
                           float *partials, int *tile_counters, float *out_h, int *out_sweeps, void *stream) {
   if (!tile_counters || engine != APAP_GRAM_TCGEN05) {     // plain sequence: K2 starts when K1 has finished
-    int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, engine, partials, stream);
+    int rc = apap_gram_partials(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, engine, t_bound, partials, stream);
     if (rc) return rc;
     return apap_eig_denorm(partials, tmats, batch, cells, make_gram_plan(cells, n_kp_padded, engine).k_splits, solver,
                            out_h, out_sweeps, stream);
@@ -96,7 +96,7 @@ int apap_local_homography(const float *kp_table, const float *anchors, const dou
   if (!partials || !tmats || !out_h) return fail(APAP_E_BADARG, "null pointer");
   if (solver != APAP_EIG_AUTO && solver != APAP_EIG_JACOBI) return fail(APAP_E_BADARG, "eig: unknown solver");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, partials, tile_counters, st);
+  rc = launch_gram_tc(kp_table, anchors, batch, cells, n_kp_padded, gamma_sq, t_bound, partials, tile_counters, st);
   if (rc) return rc;
   return launch_eig(partials, tmats, batch, cells, make_gram_plan(cells, n_kp_padded, engine).k_splits, out_h, out_sweeps,
                     solver == APAP_EIG_JACOBI, tile_counters, st);

@@ -47,7 +47,7 @@ int check_cuda(cudaError_t e, const char *what);
 int launch_gram(const float *kp_table, const float *anchors, int batch, int cells, int n_kp_padded,
                 float gamma_sq, float *partials, cudaStream_t st);
 int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded,
-                   float gamma_sq, float *partials, int *tile_done, cudaStream_t st);
+                   float gamma_sq, const float *t_bound, float *partials, int *tile_done, cudaStream_t st);
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int k_splits,
                float *out_h, int *out_sweeps, int force_jacobi, int *tile_done, cudaStream_t st);
 int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
@@ -58,6 +58,8 @@ int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast
                 size_t out_band_bytes, int flags, int multicast, const void *tiles, cudaStream_t st);
 int launch_blend(const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n_px, cudaStream_t st);
 int launch_probe(int kind, int iters, float *sink, double *ops, cudaStream_t st);
+int launch_weight_bound(const float *src_raw, const int *counts, int batch, int n_points, double scale,
+                        const float *anchors, int cells, float *t_bound, cudaStream_t st);
 int launch_multicast_copy(const void *src, void *mc_dst, size_t bytes, cudaStream_t st);
 int launch_peer_copy(const void *src, void *const *peers, int n_peers, size_t bytes, cudaStream_t st);
 

@@ -41,6 +41,8 @@
 // restart from zero; the per-split sums (<= 1024 keypoints, like the FFMA2 kernel) are written as
 // the same partial-sum layout and combined in float64 by K2.  Measured against a float64-accumulated
 // reference: 5e-7 mean / 7e-6 max of the largest sum per term (tools/gram_tc_lab.cu).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace apap {
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
                                                                       const float *__restrict__ anchors, int cells,
                                                                       int cells_padded, int n_kb, int kb_per_split,
                                                                       int k_splits, float gamma_sq,
+                                                                      const float *__restrict__ t_bound,
                                                                       float *__restrict__ partials,
                                                                       int *__restrict__ tile_done) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -276,6 +279,12 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
       if (lane == 0) mbar_arrive(&sm.d_empty);
       ++seg_done;
     };
+    // The clamp max(w, gamma^2) costs 16 of the ~180 instructions of a step.  When the caller's bound on |s v - s x| over
+    // the whole scene (apap_weight_bound) shows that no pair reaches it, the same loop runs without -- same bits, the
+    // max and the min were no-ops (margin 0.1 % + 1e-3 on t against the 2^-22 of MUFU.EX2 and the 1.6e-7 of the polynomial).
+    const bool no_clamp = t_bound && fmaf(__ldg(t_bound + scene), 1.001f, 1e-3f) < (kPoly > 0 ? t_max : -__log2f(gamma_sq));
+    auto steps = [&](auto no_clamp_tag) {
+    constexpr bool kNoClamp = decltype(no_clamp_tag)::value;
     for (int s = h; s < n_step; s += kParities) {  // the steps of this warp
       const int it = s / kSlots, g = s % kSlots;   // stage index = use count of the slot; slot
       const int ss = it % kSmemStages;
@@ -307,7 +316,8 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
 #else
           if (kPoly > 0 && k >= 4 - kPoly) {
             // 2^-min(t, t_max) by a degree-7 polynomial in u = t - 1 on [-1, 1] (max relative error 1.6e-7)
-            const float2 u = __fadd2_rn(make_float2(fminf(sqrt_approx(d2.x), t_max), fminf(sqrt_approx(d2.y), t_max)),
+            const float2 u = __fadd2_rn(kNoClamp ? make_float2(sqrt_approx(d2.x), sqrt_approx(d2.y))
+                                                        : make_float2(fminf(sqrt_approx(d2.x), t_max), fminf(sqrt_approx(d2.y), t_max)),
                                         make_float2(-1.f, -1.f));
             float2 pp = __ffma2_rn(make_float2(-7.525117780e-06f, -7.525117780e-06f), u, make_float2(7.831371477e-05f, 7.831371477e-05f));
             pp = __ffma2_rn(pp, u, make_float2(-6.669662544e-04f, -6.669662544e-04f));
@@ -319,8 +329,8 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
             w[8 * e + 2 * k] = pp.x;
             w[8 * e + 2 * k + 1] = pp.y;
           } else {
-            w[8 * e + 2 * k] = fmaxf(ex2_approx(-sqrt_approx(d2.x)), gamma_sq);
-            w[8 * e + 2 * k + 1] = fmaxf(ex2_approx(-sqrt_approx(d2.y)), gamma_sq);
+            w[8 * e + 2 * k] = kNoClamp ? ex2_approx(-sqrt_approx(d2.x)) : fmaxf(ex2_approx(-sqrt_approx(d2.x)), gamma_sq);
+            w[8 * e + 2 * k + 1] = kNoClamp ? ex2_approx(-sqrt_approx(d2.y)) : fmaxf(ex2_approx(-sqrt_approx(d2.y)), gamma_sq);
           }
 #endif
         }
@@ -355,6 +365,8 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
       // a segment behind: its MMAs have had a step's worth of time to retire
       if ((s & (kSegSteps - 1)) == h && s >= kSegSteps) drain();
     }
+    };
+    if (no_clamp) steps(std::true_type{}); else steps(std::false_type{});
     while (seg_done < n_seg) drain();
     if (c < cells) {
       // partials[split][t][cell]: consecutive threads write consecutive cells (coalesced); a thread writes
@@ -372,40 +384,44 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
     // bytes between the two 16-byte K chunks of a row = 1024, SBO (bits 32-45) = bytes between 8-row groups = 128,
     // bits 46-47 = descriptor version 1 (sm_100); the start address (>> 4) goes in bits 0-13
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(1024 >> 4) << 16);
-    int step = 0;
-    for (int st = 0; st < n_stage; ++st) {
-      const int ss = st % kSmemStages;
-      mbar_wait(&sm.smem_full[ss], (st / kSmemStages) & 1);
-      // B tile of a k-block: rows 0..31 = Ph, rows 32..63 = Pl
-      uint64_t b = desc_hi | (uint64_t)((smem_u32(sm.stage[ss]) & 0x3FFFFu) >> 4);
-#pragma unroll
-      for (int g = 0; g < kSlots; ++g, ++step) {   // slot g = step parity
-        if (lane == 0) TRACE(2, step, 0);
-        mbar_wait(&sm.a_full[g], st & 1);
-        if (lane == 0) TRACE(2, step, 1);
-        const int in_seg = step & (kSegSteps - 1);
-        if (in_seg == 0 && step > 0) mbar_wait(&sm.d_empty, ((step / kSegSteps) - 1) & 1);   // previous segment drained
+    // One elected thread runs the whole loop (no per-step ELECT / reconvergence), one stage = both A slots per round:
+    // the two producer parities finish their steps within ~50 cycles of each other (profiles/r01_gram_tc_trace.txt),
+    // and this warp shares its scheduler with the producers of lane quarter 0 -- every instruction it does not issue
+    // is a slot for the quarter the other three wait for.
+    if (elect_one()) {
+      for (int st = 0; st < n_stage; ++st) {
+        const int ss = st % kSmemStages;
+        mbar_wait(&sm.smem_full[ss], (st / kSmemStages) & 1);
+        mbar_wait(&sm.a_full[0], st & 1);
+        const int step = st * kSlots;
+        const int in_seg = step & (kSegSteps - 1);                 // kSegSteps is even: a segment starts on slot 0 ...
+        if (in_seg == 0 && st > 0) mbar_wait(&sm.d_empty, ((step / kSegSteps) - 1) & 1);   // previous segment drained
         tc_fence_after();
-        if (elect_one()) {
+        // B tile of a k-block: rows 0..31 = Ph, rows 32..63 = Pl
+        uint64_t b = desc_hi | (uint64_t)((smem_u32(sm.stage[ss]) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int g = 0; g < kSlots; ++g) {           // slot g = step parity
+          if (g) {
+            mbar_wait(&sm.a_full[g], st & 1);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int e = 0; e < kStepKb; ++e, b += kKbBytes >> 4) {
             const uint32_t a_hi = tmem_a + g * 32 + e * 16, a_lo = a_hi + 8;
-            const uint32_t fresh = (in_seg == 0 && e == 0) ? 0u : 1u;
+            const uint32_t fresh = (in_seg == 0 && g == 0 && e == 0) ? 0u : 1u;
             // D[0:32] (+)= hi . Ph and D[32:64] (+)= hi . Pl in one N = 64 MMA, then D[32:64] += lo . Ph:
             // the cross terms never touch the columns of the big sums
             mma_tf32_ts(tmem_d, a_hi, b, idesc64, fresh);
             mma_tf32_ts(tmem_d + kNT, a_lo, b, idesc32, 1u);
           }
-          mma_commit(&sm.a_empty[g]);              // the A columns are free when these retire
-          if (in_seg == kSegSteps - 1 || step == n_step - 1) mma_commit(&sm.d_full);
-          if (g == kSlots - 1) mma_commit(&sm.smem_empty[ss]);   // ... and so is the shared-memory stage
-        } else {
-          b += (uint64_t)kStepKb * (kKbBytes >> 4);
+          mma_commit(&sm.a_empty[g]);                // the A columns are free when these retire
         }
-        __syncwarp();
-        if (lane == 0) TRACE(2, step, 2);
+        // ... and ends on slot 1
+        if (in_seg == kSegSteps - kSlots || st == n_stage - 1) mma_commit(&sm.d_full);
+        mma_commit(&sm.smem_empty[ss]);              // ... and so is the shared-memory stage
       }
     }
+    __syncwarp();
   } else {
     // ================= TMA producer (one thread) =============================================
     if (lane == 0) {
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
 }
 
 int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int cells, int n_kp_padded, float gamma_sq,
-                   float *partials, int *tile_done, cudaStream_t st) {
+                   const float *t_bound, float *partials, int *tile_done, cudaStream_t st) {
   const GramPlan p = make_gram_plan(cells, n_kp_padded, APAP_GRAM_TCGEN05);
   const int n_kb = n_kp_padded / kKB;
   const int kb_per_split = p.chunks_per_split * (kChunk / kKB);
@@ -438,10 +454,10 @@ int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int 
   if (grid.y > 65535 || batch > 65535) return fail(APAP_E_TOOBIG, "gram: more than 65535 cell tiles (8.3 M cells) or scenes per launch");
   if (APAP_TC_POLY > 0 && gamma_sq >= 0.25f && gamma_sq <= 1.f)   // the polynomial covers 2^-t for t in [0, 2]
     k_gram_tc<APAP_TC_POLY><<<grid, kTcThreads, sizeof(TcSmem), st>>>(kp_blocks, anchors, cells, p.cells_padded, n_kb,
-                                                                      kb_per_split, p.k_splits, gamma_sq, partials, tile_done);
+                                                                      kb_per_split, p.k_splits, gamma_sq, t_bound, partials, tile_done);
   else
     k_gram_tc<0><<<grid, kTcThreads, sizeof(TcSmem), st>>>(kp_blocks, anchors, cells, p.cells_padded, n_kb, kb_per_split,
-                                                           p.k_splits, gamma_sq, partials, tile_done);
+                                                           p.k_splits, gamma_sq, t_bound, partials, tile_done);
   return check_cuda(cudaGetLastError(), "k_gram_tc launch");
 }
 

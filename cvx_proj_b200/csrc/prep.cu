@@ -454,6 +454,58 @@ int launch_inv_grid(const float *h, int cells, float *out, unsigned char *flags,
   return check_cuda(cudaGetLastError(), "k_inv_grid launch");
 }
 
+// ------------------------------------------------------------------------------------ k_weight_bound
+// t_bound[scene] >= |s v - s x| for every (anchor v, keypoint x) of the scene: the diagonal of the two sets' bounding
+// boxes taken together.  K1 drops the clamp max(w, gamma^2) for a scene whose bound shows that no weight reaches it.
+__global__ void __launch_bounds__(512) k_weight_bound(const float2 *__restrict__ src_raw, const int *__restrict__ counts,
+                                                      int n_points, double scale, const float2 *__restrict__ anchors,
+                                                      int cells, float *__restrict__ t_bound) {
+  const int scene = blockIdx.x, tid = threadIdx.x;
+  const int n = counts ? min(max(counts[scene], 0), n_points) : n_points;
+  src_raw += (size_t)scene * n_points;
+  anchors += (size_t)scene * cells;
+  float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < n; i += 512) {
+    const float2 v = src_raw[i];
+    lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
+    lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
+  }
+  for (int i = tid; i < cells; i += 512) {
+    const float2 v = anchors[i];
+    lo[2] = fminf(lo[2], v.x); hi[2] = fmaxf(hi[2], v.x);
+    lo[3] = fminf(lo[3], v.y); hi[3] = fmaxf(hi[3], v.y);
+  }
+  __shared__ float red[2][4][16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if ((tid & 31) == 0) { red[0][k][tid >> 5] = lo[k]; red[1][k][tid >> 5] = hi[k]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      for (int w = 1; w < 16; ++w) { lo[k] = fminf(lo[0 + k], red[0][k][w]); hi[k] = fmaxf(hi[k], red[1][k][w]); }
+    // keypoints go into the table as float(s * x): the same product here, in double, then the widest gap per axis
+    const double kx0 = scale * lo[0], kx1 = scale * hi[0], ky0 = scale * lo[1], ky1 = scale * hi[1];
+    const double dx = fmax(fabs(kx1 - lo[2]), fabs(hi[2] - kx0)), dy = fmax(fabs(ky1 - lo[3]), fabs(hi[3] - ky0));
+    const double t = sqrt(dx * dx + dy * dy) * (1.0 + 1e-6);
+    // no keypoints or no cells, NaN or infinite coordinates: no bound (+inf keeps the clamp)
+    t_bound[scene] = (n > 0 && cells > 0 && isfinite(t)) ? (float)t + 1e-6f : INFINITY;
+  }
+}
+
+int launch_weight_bound(const float *src_raw, const int *counts, int batch, int n_points, double scale,
+                        const float *anchors, int cells, float *t_bound, cudaStream_t st) {
+  k_weight_bound<<<batch, 512, 0, st>>>(reinterpret_cast<const float2 *>(src_raw), counts, n_points, scale,
+                                        reinterpret_cast<const float2 *>(anchors), cells, t_bound);
+  return check_cuda(cudaGetLastError(), "k_weight_bound launch");
+}
+
 }  // namespace apap
 
 using namespace apap;
@@ -471,6 +523,16 @@ int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_
   if (reinterpret_cast<uintptr_t>(kp_table) & 15u) return fail(APAP_E_ALIGN, "kp_rows: kp_table must be 16-byte aligned");
   return launch_kp_rows(src_cond, dst_cond, src_raw, counts, batch, n_points, n_kp_padded, scale, kp_table,
                         static_cast<cudaStream_t>(stream));
+}
+
+int apap_weight_bound(const float *src_raw, const int *counts, int batch, int n_points, double scale,
+                      const float *anchors, int cells, float *t_bound, void *stream) {
+  if (!src_raw || !anchors || !t_bound) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || n_points <= 0 || cells <= 0 || batch > 65535) return fail(APAP_E_BADARG, "weight_bound: bad sizes");
+  if ((reinterpret_cast<uintptr_t>(src_raw) | reinterpret_cast<uintptr_t>(anchors)) & 7u)
+    return fail(APAP_E_ALIGN, "weight_bound: the point arrays must be 8-byte aligned");
+  return launch_weight_bound(src_raw, counts, batch, n_points, scale, anchors, cells, t_bound,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int apap_condition(const float *src, const float *dst, const int *counts, int batch, int n_points, float *cond,

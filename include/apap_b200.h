@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 19
+#define APAP_ABI_VERSION 20
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -79,9 +79,15 @@ int apap_gram_plan(int cells, int n_kp_padded, int engine, int *k_splits, int *c
  *   anchors  : float [batch][cells][2] = s * (x, y) of the cell anchor points (get_vertice)
  *   partials : float [batch][k_splits][24][cells_padded]  (same layout for both engines)
  *   gamma_sq = gamma^2
+ *   t_bound  : optional float [batch] from apap_weight_bound (device memory): an upper bound of |s v - s x| over
+ *              the scene's (anchor, keypoint) pairs.  Engine TCGEN05 drops the clamp max(w, gamma^2) of
+ *              pyviz/apap.py:152 for a scene whose bound shows no weight can reach it (1.001 t + 0.001 <
+ *              -log2 gamma^2; the reference's gamma = 0.5, sigma = 100 on a 4K canvas is such a scene): the same
+ *              bits, 16 of ~180 instructions per 16 keypoints less.  NULL = always clamp.
  */
 int apap_gram_partials(const float *kp_table, const float *anchors, int batch, int cells,
-                       int n_kp_padded, float gamma_sq, int engine, float *partials, void *stream);
+                       int n_kp_padded, float gamma_sq, int engine, const float *t_bound, float *partials,
+                       void *stream);
 
 /*
  * K2 -- per-cell 9x9 symmetric eigensolve + de-normalisation.  Replaces cv.SVDecomp + V[-1]
@@ -110,7 +116,8 @@ int apap_eig_denorm(const float *partials, const double *tmats, int batch, int c
  */
 int apap_local_homography(const float *kp_table, const float *anchors, const double *tmats,
                           int batch, int cells, int n_kp_padded, float gamma_sq, int engine, int solver,
-                          float *partials, int *tile_counters, float *out_h, int *out_sweeps, void *stream);
+                          const float *t_bound, float *partials, int *tile_counters, float *out_h, int *out_sweeps,
+                          void *stream);
 
 /*
  * Second output of APAP.local_homography (pyviz/apap.py:144,153): float64 weights
@@ -250,6 +257,17 @@ int apap_invert_grid(const float *grid, int cells, float *grid_inv, unsigned cha
  */
 int apap_condition(const float *src, const float *dst, const int *counts, int batch, int n_points, float *cond,
                    float *mats, double *tmats, void *stream);
+
+/*
+ * apap_weight_bound: t_bound[scene] = an upper bound of |s v - s x| over the scene's cell anchors v and matched source
+ * points x (the distance of pyviz/apap.py:150-151 in the pre-scaled units of K1): the diagonal of the two sets' joint
+ * bounding box, rounded up; +inf for a scene without points or with non-finite coordinates.  The `t_bound` of
+ * apap_gram_partials / apap_local_homography.
+ *   src_raw : float [batch][n_points][2] raw source points;  counts : int32 [batch] or NULL;  scale = s
+ *   anchors : float [batch][cells][2] = s * anchor (the `anchors` of K1);  t_bound : out float [batch]
+ */
+int apap_weight_bound(const float *src_raw, const int *counts, int batch, int n_points, double scale,
+                      const float *anchors, int cells, float *t_bound, void *stream);
 
 int apap_kp_rows(const float *src_cond, const float *dst_cond, const float *src_raw, const int *counts, int batch,
                  int n_points, int n_kp_padded, double scale, float *kp_table, void *stream);

@@ -183,6 +183,55 @@ def test_overlapped_k2_launch_equals_plain_sequence():
         assert int(st._tile_counters(torch, dev, batch, sc.n_cells).abs().sum().item()) == 0
 
 
+def test_clamp_free_k1_path_is_bit_identical_and_the_bound_is_an_upper_bound():
+    """apap_weight_bound bounds the pre-scaled distance of every (cell, match) pair; with it K1 leaves the clamp
+    max(w, gamma^2) out where no weight can reach it (reference defaults on c1 / c2) and keeps it where some do (small
+    sigma) -- the H grid has the same bits as the always-clamping launch either way, and as a launch told +inf."""
+    import torch
+    from cvx_proj_b200.apap import scale_anchors, weight_scale
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for name, kw, clamp_free in (("c1", {}, True), ("c2", {}, True), ("c1", {"sigma": 8.5}, False),
+                                 ("mini", {"sigma": 30.0, "gamma": 0.1}, True), ("mini", {"sigma": 10.0, "gamma": 0.1}, False)):
+        sc = synth.make_scene(name)
+        st = _stitcher(sc, **kw)
+        table, tmats = st._prepare(sc.src, sc.dst)
+        s = weight_scale(st.sigma)
+        t = st.kp_table_device(torch.from_numpy(table[None]).to(dev))
+        anchors = scale_anchors(sc.vertices, s)
+        a = torch.from_numpy(anchors[None]).to(dev)
+        m = torch.from_numpy(tmats[None]).to(dev)
+        raw = torch.from_numpy(np.ascontiguousarray(sc.src[None], dtype=np.float32)).to(dev)
+        bound = st.weight_bound_device(raw, None, a)
+        # the largest pre-scaled distance any pair really has (float64)
+        flat = anchors.reshape(-1, 2).astype(np.float64)
+        some = np.concatenate([flat[::97], flat[[0, sc.mesh_cells - 1, -sc.mesh_cells, -1]]])
+        d = np.float64(s) * sc.src.astype(np.float64)[None] - some[:, None]
+        true_max = np.sqrt((d ** 2).sum(-1)).max()
+        k = np.float64(s) * sc.src.astype(np.float64)
+        box = np.hypot(max(k[:, 0].max() - flat[:, 0].min(), flat[:, 0].max() - k[:, 0].min()),
+                       max(k[:, 1].max() - flat[:, 1].min(), flat[:, 1].max() - k[:, 1].min()))
+        got_bound = float(bound.item())
+        assert true_max <= got_bound and box <= got_bound <= box * 1.0001 + 2e-6
+        t_max = -np.log2(np.float32(st.gamma) ** 2)
+        limit = min(t_max, 2.0) if np.float32(st.gamma) ** 2 >= 0.25 else t_max      # the polynomial 2^-t covers t <= 2
+        assert (got_bound * 1.001 + 1e-3 < limit) == clamp_free
+        plain = st.local_homography_device(t, a, m, 1, sc.n_cells).cpu().numpy()
+        with_bound = st.local_homography_device(t, a, m, 1, sc.n_cells, t_bound=bound).cpu().numpy()
+        inf = torch.full((1,), float("inf"), dtype=torch.float32, device=dev)
+        with_inf = st.local_homography_device(t, a, m, 1, sc.n_cells, t_bound=inf).cpu().numpy()
+        assert np.array_equal(plain.view(np.uint32), with_bound.view(np.uint32))
+        assert np.array_equal(plain.view(np.uint32), with_inf.view(np.uint32))
+    # counts: matches past a scene's count do not widen its box; a scene without matches gets +inf
+    pts = torch.tensor([[[10.0, 20.0], [30.0, 5.0], [9000.0, 9000.0]], [[1.0, 1.0], [2.0, 2.0], [3.0, 3.0]]], device=dev)
+    counts = torch.tensor([2, 0], dtype=torch.int32, device=dev)
+    anch = torch.tensor([[[0.0, 0.0], [0.04, 0.02]]] * 2, device=dev)
+    st = APAP(0.5, 100, [64, 64], [0, 0])
+    b = st.weight_bound_device(pts, counts, anch).cpu().numpy()
+    s = weight_scale(100)
+    want = np.hypot(max(abs(30 * s - 0.0), abs(0.04 - 10 * s)), max(abs(20 * s - 0.0), abs(0.02 - 5 * s)))
+    assert np.isinf(b[1]) and want <= b[0] <= want * 1.0001 + 2e-6
+
+
 def test_gram_engines_agree_on_partial_sums():
     """The tensor-core (3xTF32, TMEM) and the FP32 SIMT Gram kernels produce the same partial sums to
     ~1e-6 of the largest sum of each term (tcgen05 accumulates per 256-keypoint segment)."""
@@ -199,7 +248,7 @@ def test_gram_engines_agree_on_partial_sums():
         ks, cp, nbytes = rt.gram_plan(cells, n_pad, engine)
         t = torch.from_numpy(tab).to(dev)
         part = torch.zeros(nbytes // 4, dtype=torch.float32, device=dev)
-        rt.check(lib.apap_gram_partials(t.data_ptr(), a.data_ptr(), 1, cells, n_pad, 0.25, engine, part.data_ptr(),
+        rt.check(lib.apap_gram_partials(t.data_ptr(), a.data_ptr(), 1, cells, n_pad, 0.25, engine, None, part.data_ptr(),
                                         rt.stream_ptr(torch, dev)), "gram")
         out[engine] = part.cpu().numpy().reshape(ks, 24, cp)[:, :, :cells].astype(np.float64).sum(0)
     ref, got = out[rt.GRAM_FFMA2], out[rt.GRAM_TCGEN05]

@@ -35,7 +35,7 @@ for spec in sys.argv[1:]:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         rt.check(lib.apap_gram_partials(t_dev.data_ptr(), a_dev.data_ptr(), 1, cells, n_pad, 0.25, rt.GRAM_TCGEN05,
-                                        partials.data_ptr(), s), "gram")
+                                        None, partials.data_ptr(), s), "gram")
         e1.record(); e1.synchronize()
         if k >= 3:
             ts.append(e0.elapsed_time(e1) * 1e3)

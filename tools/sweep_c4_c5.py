@@ -51,7 +51,7 @@ for n_kp in (1000, 2000, 4000, 8000, 16000, 32000, 64000):
     lib, s = rt.load_library(), rt.stream_ptr(torch, dev)
     g2 = float(np.float32(sc.gamma ** 2))
     ms_gram = timed(lambda: rt.check(lib.apap_gram_partials(t_dev.data_ptr(), a_dev.data_ptr(), 1, cells, n_pad, g2,
-                                                            rt.GRAM_TCGEN05, partials.data_ptr(), s)))
+                                                            rt.GRAM_TCGEN05, None, partials.data_ptr(), s)))
     ms_eig = timed(lambda: rt.check(lib.apap_eig_denorm(partials.data_ptr(), m_dev.data_ptr(), 1, cells, ks,
                                                         rt.EIG_AUTO, out_h.data_ptr(), None, s)))
     ms_both = timed(lambda: st.local_homography_device(t_dev, a_dev, m_dev, 1, cells, out_h=out_h, partials=partials))
