@@ -81,7 +81,8 @@ constexpr int kProducerWarps = 4 * kParities;
 constexpr int kMmaWarp = kProducerWarps, kTmaWarp = kProducerWarps + 1;
 constexpr int kTcThreads = (kProducerWarps + 2) * 32;
 constexpr int kTcCtasPerSm = kParities == 1 ? 4 : 3;
-static_assert(kParities == 1 || kParities == 2, "one or two producer warps per lane quarter");
+static_assert(kParities == 2 && kParities == kSlots, "two producer warps per lane quarter, each with its own A slot");
+static_assert((kSmemStages & (kSmemStages - 1)) == 0, "the ring position is a mask of the stage index");
 static_assert(kKbFloats == 2 * kNT * kKB + 2 * kKB, "k-block layout");
 static_assert((kChunk / kKB) % kStageKb == 0, "a split is a whole number of stages");
 static_assert(kStageKb / kStepKb == kSlots && kSlots == 2, "one step per producer parity in a stage");
@@ -102,6 +103,38 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok;
 }
+// the same on shared-window addresses (the producers' loop keeps them in registers)
+__device__ __forceinline__ uint32_t mbar_test_at(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
@@ -116,6 +149,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -283,24 +324,28 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
     // the whole scene (apap_weight_bound) shows that no pair reaches it, the same loop runs without -- same bits, the
     // max and the min were no-ops (margin 0.1 % + 1e-3 on t against the 2^-22 of MUFU.EX2 and the 1.6e-7 of the polynomial).
     const bool no_clamp = t_bound && fmaf(__ldg(t_bound + scene), 1.001f, 1e-3f) < (kPoly > 0 ? t_max : -__log2f(gamma_sq));
+    const uint32_t slot = tmem_a + lane_base + h * 32;
+    const uint32_t bar_full0 = smem_u32(&sm.smem_full[0]);
+    const uint32_t bar_a_empty = smem_u32(&sm.a_empty[h]), bar_a_full = smem_u32(&sm.a_full[h]);
+    const uint32_t co0 = smem_u32(sm.stage[0]) + (2 * kNT * kKB + h * kStepKb * kKbFloats) * 4;   // the step's coordinates
     auto steps = [&](auto no_clamp_tag) {
     constexpr bool kNoClamp = decltype(no_clamp_tag)::value;
-    for (int s = h; s < n_step; s += kParities) {  // the steps of this warp
-      const int it = s / kSlots, g = s % kSlots;   // stage index = use count of the slot; slot
-      const int ss = it % kSmemStages;
-      const uint32_t slot = tmem_a + lane_base + g * 32;
+    // this warp's step of stage `it` is s = 2 it + h: slot h of the A ring is its own (kParities == kSlots), and every
+    // shared-memory address of the loop is a constant plus a multiple of the ring position
+    for (int it = 0; it < n_stage; ++it) {
+      const uint32_t ss = (uint32_t)it & (kSmemStages - 1);
       if (q == 0 && lane == 0) TRACE(h, it, 0);
-      if (kParities == 2 || g == 0) mbar_wait(&sm.smem_full[ss], (it / kSmemStages) & 1);
+      mbar_wait_at(bar_full0 + 8 * ss, ((uint32_t)it / kSmemStages) & 1);
       const uint32_t a_par = (it & 1) ^ 1;         // first use of the slot: free
 #if APAP_TC_EARLY_PROBE
-      const uint32_t slot_free = mbar_test(&sm.a_empty[g], a_par);   // consumed after the arithmetic
+      const uint32_t slot_free = mbar_test_at(bar_a_empty, a_par);   // consumed after the arithmetic
 #endif
       if (q == 0 && lane == 0) TRACE(h, it, 1);
-      const float4 *co = reinterpret_cast<const float4 *>(sm.stage[ss] + 2 * kNT * kKB) + g * kStepKb * (kKbFloats / 4);
+      uint32_t co = co0 + ss * kStageBytesTc;
       float w[kStepKb * 8];
 #pragma unroll
-      for (int e = 0; e < kStepKb; ++e, co += kKbFloats / 4) {
-        const float4 x0 = co[0], x1 = co[1], y0 = co[2], y1 = co[3];
+      for (int e = 0; e < kStepKb; ++e, co += kKbBytes) {
+        const float4 x0 = lds128(co), x1 = lds128(co + 16), y0 = lds128(co + 32), y1 = lds128(co + 48);
         const float2 kx[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y),
                               make_float2(x1.z, x1.w)};
         const float2 ky[4] = {make_float2(y0.x, y0.y), make_float2(y0.z, y0.w), make_float2(y1.x, y1.y),
@@ -336,34 +381,33 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
         }
       }
 #if APAP_TC_EARLY_PROBE
-      if (!slot_free) mbar_wait(&sm.a_empty[g], a_par);
+      if (!slot_free) mbar_wait_at(bar_a_empty, a_par);
 #else
-      mbar_wait(&sm.a_empty[g], a_par);
+      mbar_wait_at(bar_a_empty, a_par);
 #endif
       tc_fence_after();
       if (q == 0 && lane == 0) TRACE(h, it, 2);
 #pragma unroll
       for (int e = 0; e < kStepKb; ++e) {
-        uint32_t hi[8], lo[8];
+        uint32_t hl[16];                               // TF32 heads, then tails: the 16 A columns of k-block e
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {               // lo = w - hi (exact), two at a time on the packed FP32x2 adder
-          hi[k] = tf32_head(w[8 * e + k]);
-          hi[k + 1] = tf32_head(w[8 * e + k + 1]);
+          hl[k] = tf32_head(w[8 * e + k]);
+          hl[k + 1] = tf32_head(w[8 * e + k + 1]);
           const float2 l = __fadd2_rn(make_float2(w[8 * e + k], w[8 * e + k + 1]),
-                                      make_float2(-__uint_as_float(hi[k]), -__uint_as_float(hi[k + 1])));
-          lo[k] = __float_as_uint(l.x);
-          lo[k + 1] = __float_as_uint(l.y);
+                                      make_float2(-__uint_as_float(hl[k]), -__uint_as_float(hl[k + 1])));
+          hl[8 + k] = __float_as_uint(l.x);
+          hl[8 + k + 1] = __float_as_uint(l.y);
         }
-        tmem_st8(slot + e * 16, hi);
-        tmem_st8(slot + e * 16 + 8, lo);
+        tmem_st16(slot + e * 16, hl);
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.a_full[g]);
+      if (lane == 0) mbar_arrive_at(bar_a_full);
       if (q == 0 && lane == 0) TRACE(h, it, 3);
       // a segment behind: its MMAs have had a step's worth of time to retire
-      if ((s & (kSegSteps - 1)) == h && s >= kSegSteps) drain();
+      if ((it & (kSegKb / kStageKb - 1)) == 0 && it) drain();
     }
     };
     if (no_clamp) steps(std::true_type{}); else steps(std::false_type{});
