@@ -57,6 +57,9 @@ namespace apap {
 #ifndef APAP_TC_POLY
 #define APAP_TC_POLY 2           // weight pairs per k-block (of 4) whose 2^-t runs on the FMA pipe when gamma^2 >= 1/4
 #endif
+#ifndef APAP_TC_UNROLL
+#define APAP_TC_UNROLL 8          // producer loop unrolled over the ring positions and slot phases: addresses and parities are immediates (1: 131 us, 4: 128, 8: 125, 16: 126 at c2)
+#endif
 #ifndef APAP_TC_EARLY_PROBE
 #define APAP_TC_EARLY_PROBE 1    // 0: wait for the A slot before the step's arithmetic (A/B timing)
 #endif
@@ -69,6 +72,7 @@ constexpr int kStepKb = 2;                         // k-blocks per producer/MMA 
 constexpr int kStageKb = 4;                        // k-blocks per shared-memory stage (2 steps: one per producer parity)
 constexpr int kStageBytesTc = kStageKb * kKbBytes; // 8448
 constexpr int kSmemStages = APAP_TC_SMEM_STAGES;
+constexpr int kUnroll = APAP_TC_UNROLL;
 constexpr int kSlots = 2;                          // A slots in TMEM: slot h = steps of parity h, 2 k-blocks x (8 hi + 8 lo columns)
 constexpr int kTmemCols = 128;                     // 32 (D1) + 32 (D2) + 2 * 32 (A)
 constexpr int kSegKb = 32;                         // k-blocks per accumulation segment (256 keypoints)
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) k_gram_tc(const floa
     constexpr bool kNoClamp = decltype(no_clamp_tag)::value;
     // this warp's step of stage `it` is s = 2 it + h: slot h of the A ring is its own (kParities == kSlots), and every
     // shared-memory address of the loop is a constant plus a multiple of the ring position
+#pragma unroll kUnroll
     for (int it = 0; it < n_stage; ++it) {
       const uint32_t ss = (uint32_t)it & (kSmemStages - 1);
       if (q == 0 && lane == 0) TRACE(h, it, 0);
