@@ -33,6 +33,16 @@
 // instead of 4 CTAs x 4) -3.5 %, the slot probe (mbarrier.test_wait) issued before the step's arithmetic
 // and consumed after it -1 %, half of the 2^-t on the FMA pipe -4..6 %, truncating split instead of a
 // rounding one -5 %; the depth of the A ring, of the shared-memory ring and the TMA latency do not matter.
+// Round 2 (profiles/r02_gram_variants.txt; c2, same box per comparison): the kernel answers to its instruction count --
+// a step of 16 keypoints was ~180 instructions per producer warp for 24 MUFU, and every 16 instructions taken out are
+// ~4 % of the time.  The clamp dropped where apap_weight_bound proves it a no-op (-16 instructions, 139 -> 131 us), ring
+// addresses as shared-window constants and one 16-column tcgen05.st per k-block (-9, -> 127 us), the producer loop
+// unrolled 8x so that ring position and slot phase are immediates (-12, -> 125 us); the polynomial share stays at 2 of 4
+// (1 of 4 and 3 of 4: +3 %); the MMA warp's own instruction count does not matter (-35 % of it: no change), nor does the
+// number of keypoint splits (4 .. 8 at c2: 125 .. 127 us).  What is left between c2 (0.70 of the XU roofline) and c3
+// (0.83, 28 waves): 1252 CTAs over 444 slots leave some SMs a ninth CTA while others have done their eight, and the last
+// CTAs of an SM run alone at about half the rate of three.  Persistent CTAs would fix both but hold all the registers of
+// the SM to the end, so K2 could no longer move in beside K1's last CTAs (its 9 us exposed tail would become 16).
 //
 // Accuracy.  The tensor core accumulates in FP32 and aligns/truncates the accumulator at every
 // MMA, a drift proportional to the number of MMAs that touch a big accumulator.  So (a) only one
