@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(256) k_peer_copy(const uint4 *__restrict__ src
     const uint4 a = __ldcs(src + i);
     uint4 b = a;
     if (two) b = __ldcs(src + i + stride);
-    for (int k = 0; k < pl.n; ++k) {
-      pl.dst[k][i] = a;
-      if (two) pl.dst[k][i + stride] = b;
+#pragma unroll
+    for (int k = 0; k < APAP_MAX_PEERS; ++k) {           // unrolled: the list stays in the parameter bank
+      if (k < pl.n) {
+        pl.dst[k][i] = a;
+        if (two) pl.dst[k][i + stride] = b;
+      }
     }
   }
 }

@@ -81,7 +81,7 @@ def main():
                 "profiler: compare shares, not absolutes).\n\n" + "\n".join(out) + "\n")
     tj = os.path.join(REPO, "profiles", "ncu_traffic.json")
     allt = json.load(open(tj)) if os.path.exists(tj) else {}
-    allt.setdefault(workload, {}).update(traffic)
+    allt[workload] = traffic                       # the capture replaces the workload's table: no stale kernels of older rounds
     with open(tj, "w") as f:
         json.dump(allt, f, indent=1, sort_keys=True)
     print("wrote", md, "and", tj, traffic)

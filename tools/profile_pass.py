@@ -33,6 +33,8 @@ def gw(mode):
 for _ in range(iters):
     p.gram(); p.eig()                                   # K1, K2 one by one
     p.dlt()                                             # K1 + K2 as the public call launches them (K2 overlapped)
+    p.st.condition_device(p.points[1:3].contiguous())   # k_condition, k_condition_mats (any two point sets)
+    p.st.weight_bound_device(p.points[2], None, p.anchors[None])   # k_weight_bound
     p.st.kp_rows_device(p.points)                       # k_kp_rows
     p.st.kp_table_device(p.rows)                        # k_kp_blocks
     p.st.invert_grid(p.h_out.cpu().numpy().reshape(-1, 3, 3))   # k_inv_grid (+ copies)
