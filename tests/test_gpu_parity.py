@@ -939,3 +939,26 @@ def test_local_warp_bilinear_opt_in_within_one_lsb_of_float64_restatement(name):
     assert np.array_equal(got.any(axis=-1), nearest.any(axis=-1))           # the same pixels are written (images are >= 1)
     with pytest.raises(ValueError):
         st.local_warp(img, h.copy(), sc.mesh, interpolation="cubic")
+
+
+def test_peer_copy_writes_every_listed_buffer():
+    """apap_peer_copy (the unicast panorama assembly): every listed destination receives the band, bytes outside stay;
+    argument checks fire before anything is launched.  (Peers are buffers of this GPU here; tools/assemble_lab.py and
+    tools/check_sharded_nccl.py run it across GPUs.)"""
+    import ctypes
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lib = rt.load_library()
+    stream = rt.stream_ptr(torch, dev)
+    for n_bytes, n_peers in ((16, 1), (4096 + 16, 3), (1 << 20, 15)):
+        src = torch.randint(0, 256, (n_bytes,), dtype=torch.uint8, device=dev)
+        dsts = [torch.full((n_bytes + 32,), 7, dtype=torch.uint8, device=dev) for _ in range(n_peers)]
+        ptrs = (ctypes.c_void_p * n_peers)(*[d.data_ptr() + 16 for d in dsts])
+        rt.check(lib.apap_peer_copy(src.data_ptr(), ptrs, n_peers, n_bytes, stream), "apap_peer_copy")
+        torch.cuda.synchronize()
+        for d in dsts:
+            assert torch.equal(d[16:16 + n_bytes], src) and int(d[:16].min()) == 7 and int(d[-16:].max()) == 7
+    bad = (ctypes.c_void_p * 1)(src.data_ptr() + 8)
+    assert lib.apap_peer_copy(src.data_ptr(), bad, 1, 16, stream) != 0            # misaligned destination
+    assert lib.apap_peer_copy(src.data_ptr(), ptrs, 16, 16, stream) != 0           # more than APAP_MAX_PEERS
+    assert lib.apap_peer_copy(src.data_ptr(), ptrs, 1, 24, stream) != 0            # size not a multiple of 16
