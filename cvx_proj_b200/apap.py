@@ -129,6 +129,9 @@ def cell_lookup_tables(mesh: np.ndarray, final_w: int, final_h: int, grid_rows: 
     indexing; a pixel at or beyond the last edge makes the reference raise IndexError, so do we.
     """
     mesh_w, mesh_h = mesh
+    if grid_rows > 65535 or grid_cols > 65535:
+        raise ValueError("the warp tables hold cell indices in 16 bits: at most 65535 grid rows and columns "
+                         f"(got {grid_rows} x {grid_cols})")
     out = []
     for edges, extent, ncell in ((mesh_w, final_w, grid_cols), (mesh_h, final_h, grid_rows)):
         edges = np.asarray(edges)
@@ -458,7 +461,7 @@ class LazyLocalWeight:
     """
 
     def __init__(self, src_point, vertices, gamma, sigma, device=None):
-        self._src = np.ascontiguousarray(src_point, dtype=np.float32)
+        self._src = np.ascontiguousarray(src_point, dtype=np.float64)      # exact promotion, as in `vertices - src_point`
         self._vert = np.ascontiguousarray(vertices, dtype=np.float64)
         self._gamma = float(gamma)
         self._inv = 1.0 / (sigma ** 2)
@@ -491,9 +494,76 @@ class LazyLocalWeight:
                 out[a - r0:b - r0] = rt.to_host(torch, buf).reshape(b - a, p, n)
         return out
 
+    #: ``np.asarray(w)`` and the numpy-style operations below refuse to build more than this many bytes in one piece
+    #: (c3 is 25.6 GB, the 64k-keypoint sweep 34 GB); ``w.rows(r0, r1)`` and ``w[i]`` stream any grid slice by slice.
+    materialize_limit = 8 << 30
+
+    @property
+    def nbytes(self):
+        return int(np.prod(self.shape, dtype=np.int64)) * 8
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64))
+
     def __array__(self, dtype=None, copy=None):
+        if self.nbytes > self.materialize_limit:
+            raise MemoryError(f"local_weight is {self.nbytes / 2**30:.1f} GiB as one array (limit "
+                              f"{self.materialize_limit / 2**30:.0f} GiB, LazyLocalWeight.materialize_limit): "
+                              "read it by cell rows with .rows(r0, r1) or w[i]")
         full = self.rows(0, self.shape[0])
         return full if dtype is None else full.astype(dtype, copy=False)
+
+    # what a reference user does with the ndarray works here too: arithmetic, comparisons and numpy functions build
+    # the array once (under the limit above) and hand over to numpy
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        args = [np.asarray(a) if isinstance(a, LazyLocalWeight) else a for a in inputs]
+        return getattr(ufunc, method)(*args, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        def conv(a):
+            if isinstance(a, LazyLocalWeight):
+                return np.asarray(a)
+            if isinstance(a, (list, tuple)):
+                return type(a)(conv(v) for v in a)
+            return a
+        return func(*conv(args), **{k: conv(v) for k, v in kwargs.items()})
+
+    def sum(self, *a, **k):
+        return np.asarray(self).sum(*a, **k)
+
+    def mean(self, *a, **k):
+        return np.asarray(self).mean(*a, **k)
+
+    def min(self, *a, **k):
+        return np.asarray(self).min(*a, **k)
+
+    def max(self, *a, **k):
+        return np.asarray(self).max(*a, **k)
+
+    def astype(self, dtype, **k):
+        return np.asarray(self).astype(dtype, **k)
+
+    def copy(self):
+        return np.asarray(self).copy()
+
+    def __mul__(self, o): return np.multiply(self, o)
+    def __rmul__(self, o): return np.multiply(o, self)
+    def __add__(self, o): return np.add(self, o)
+    def __radd__(self, o): return np.add(o, self)
+    def __sub__(self, o): return np.subtract(self, o)
+    def __rsub__(self, o): return np.subtract(o, self)
+    def __truediv__(self, o): return np.true_divide(self, o)
+    def __rtruediv__(self, o): return np.true_divide(o, self)
+    def __pow__(self, o): return np.power(self, o)
+    def __neg__(self): return np.negative(self)
+    def __lt__(self, o): return np.less(self, o)
+    def __le__(self, o): return np.less_equal(self, o)
+    def __gt__(self, o): return np.greater(self, o)
+    def __ge__(self, o): return np.greater_equal(self, o)
+    def __eq__(self, o): return np.equal(self, o)
+    def __ne__(self, o): return np.not_equal(self, o)
+    __hash__ = None
 
     def __getitem__(self, key):
         if isinstance(key, tuple) and len(key) >= 1 and isinstance(key[0], (int, np.integer)):

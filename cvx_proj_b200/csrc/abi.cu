@@ -102,10 +102,11 @@ int apap_local_homography(const float *kp_table, const float *anchors, const dou
                     solver == APAP_EIG_JACOBI, tile_counters, st);
 }
 
-int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
+int apap_local_weight(const double *anchors, const double *kp_xy, int cells, int n_kp, double inv_sigma_sq,
                       double gamma, double *out, void *stream) {
   if (!anchors || !kp_xy || !out) return fail(APAP_E_BADARG, "null pointer");
   if (cells < 0 || n_kp < 0) return fail(APAP_E_BADARG, "local_weight: negative size");
+  if (reinterpret_cast<uintptr_t>(kp_xy) & 15u) return fail(APAP_E_ALIGN, "local_weight: kp_xy must be 16-byte aligned");
   return launch_weight(anchors, kp_xy, cells, n_kp, inv_sigma_sq, gamma, out, static_cast<cudaStream_t>(stream));
 }
 

@@ -50,7 +50,7 @@ int launch_gram_tc(const float *kp_blocks, const float *anchors, int batch, int 
                    float gamma_sq, const float *t_bound, float *partials, int *tile_done, cudaStream_t st);
 int launch_eig(const float *partials, const double *tmats, int batch, int cells, int k_splits,
                float *out_h, int *out_sweeps, int force_jacobi, int *tile_done, cudaStream_t st);
-int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq,
+int launch_weight(const double *anchors, const double *kp_xy, int cells, int n_kp, double inv_sigma_sq,
                   double gamma, double *out, cudaStream_t st);
 int launch_warp(const uint8_t *src, int src_h, int src_w, const float *cell_fast, const float *cell_hinv,
                 const uint32_t *col_lut, const uint32_t *row_blocks, int n_blocks, int grid_cols, int canvas_w, int off_x,

@@ -5,22 +5,23 @@
 namespace apap {
 
 // out[c][i] = max(exp(-sqrt(dx^2 + dy^2) * inv_sigma_sq), gamma) in float64, dx = anchor - keypoint
-// promoted exactly as numpy promotes float64 - float32.  Pure streaming writes (8 B / element).
-__global__ void __launch_bounds__(256) k_weight(const double *__restrict__ anchors, const float *__restrict__ kp_xy,
+// in float64 (the caller promotes float32 keypoints exactly, as numpy promotes float64 - float32).  Pure streaming
+// writes (8 B / element).
+__global__ void __launch_bounds__(256) k_weight(const double *__restrict__ anchors, const double *__restrict__ kp_xy,
                                                  int n_kp, double inv_sigma_sq, double gamma,
                                                  double *__restrict__ out) {
   const int cell = blockIdx.y;
   const double vx = anchors[2 * cell], vy = anchors[2 * cell + 1];
   double *dst = out + (size_t)cell * n_kp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_kp; i += gridDim.x * blockDim.x) {
-    const float2 k = reinterpret_cast<const float2 *>(kp_xy)[i];
-    const double dx = vx - (double)k.x, dy = vy - (double)k.y;
+    const double2 k = reinterpret_cast<const double2 *>(kp_xy)[i];
+    const double dx = vx - k.x, dy = vy - k.y;
     const double w = exp(-(sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) * inv_sigma_sq));
     dst[i] = w < gamma ? gamma : w;
   }
 }
 
-int launch_weight(const double *anchors, const float *kp_xy, int cells, int n_kp, double inv_sigma_sq, double gamma,
+int launch_weight(const double *anchors, const double *kp_xy, int cells, int n_kp, double inv_sigma_sq, double gamma,
                   double *out, cudaStream_t st) {
   if (cells == 0 || n_kp == 0) return 0;
   if (cells > 65535) return fail(APAP_E_TOOBIG, "local_weight: at most 65535 cells per call (slice the grid)");

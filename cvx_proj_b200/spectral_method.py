@@ -80,12 +80,20 @@ def affinity_diagonal(src_pts, dst_pts, c_feats, o_feats, F, epi_weight):
 
 def spectral_segment_device(src_pts, dst_pts, diag, affinity_eps, device=None, return_info=False):
     """``|U[:, 0]| / max`` of the affinity matrix (pyviz/spectral_method.py:112-125) on the GPU: matrix build +
-    power iteration.  ``src_pts`` / ``dst_pts``: float32 ``[N, 2]``; ``diag``: float64 ``[N]``."""
+    power iteration.  ``src_pts`` / ``dst_pts``: float32 ``[N, 2]``; ``diag``: float64 ``[N]``.  N <= 65535 and the dense
+    float64 matrix must fit the device (``ApapError`` otherwise); a ``RuntimeWarning`` (and ``info["converged"] = False``)
+    when the iteration has not settled in ``POWER_MAX_ITER`` steps (repeated leading eigenvalue)."""
     torch, device = rt.torch_cuda(device)
     lib = rt.load_library()
     n = int(src_pts.shape[0])
     if n == 0:
         return (np.zeros(0), {"iterations": 0}) if return_info else np.zeros(0)
+    if n > 65535:
+        raise rt.ApapError(f"spectral_segment_device: {n} matches; the dense affinity matrix kernels take at most 65535")
+    free_bytes, _ = torch.cuda.mem_get_info(device)
+    if 8 * n * n > 0.9 * free_bytes:
+        raise rt.ApapError(f"spectral_segment_device: the {n} x {n} float64 affinity matrix needs {8 * n * n / 2**30:.1f} GiB, "
+                           f"{free_bytes / 2**30:.1f} GiB are free on {device}")
     rcp_value = np.float32(1 / 2 / (affinity_eps ** 2))          # the float32 the reference's float32 product sees
     s_dev = rt.to_device(torch, device, np.ascontiguousarray(src_pts, dtype=np.float32))
     d_dev = rt.to_device(torch, device, np.ascontiguousarray(dst_pts, dtype=np.float32))
@@ -96,7 +104,7 @@ def spectral_segment_device(src_pts, dst_pts, diag, affinity_eps, device=None, r
     norms = torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64, device=device)   # ring of |y_k|^2
     x = torch.empty(n, dtype=torch.float64, device=device)
     diff = torch.zeros(1, dtype=torch.int64, device=device)     # bits of a non-negative double
-    iters = 0
+    iters, converged, last = 0, True, float("inf")
     with torch.cuda.device(device):
         st = rt.stream_ptr(torch, device)
         rt.check(lib.apap_affinity_matrix(s_dev.data_ptr(), d_dev.data_ptr(), g_dev.data_ptr(), n, float(rcp_value),
@@ -105,12 +113,22 @@ def spectral_segment_device(src_pts, dst_pts, diag, affinity_eps, device=None, r
             rt.check(lib.apap_power_iterate(m.data_ptr(), n, y.data_ptr(), norms.data_ptr(), iters, POWER_CHECK_EVERY,
                                             x.data_ptr(), diff.data_ptr(), st), "apap_power_iterate")
             iters += POWER_CHECK_EVERY
-            if diff.view(torch.float64).item() <= POWER_TOL:
+            last = diff.view(torch.float64).item()
+            if last <= POWER_TOL:
                 break
+        else:
+            # two (nearly) equal leading eigenvalues -- e.g. two disjoint, equally consistent clusters of matches: the
+            # iterate is a mixture of their vectors, where np.linalg.svd returns one of them.  Say so instead of
+            # handing it over silently (info["converged"] carries the same for return_info callers).
+            import warnings
+            warnings.warn(f"spectral_segment_device: power iteration stopped at {iters} steps with max|dx| = {last:.2e} "
+                          f"(> {POWER_TOL:g}); the leading eigenvalue of the affinity matrix is (nearly) repeated and the "
+                          "scores are a mixture of its eigenvectors", RuntimeWarning, stacklevel=2)
+            converged = False
     seg = np.abs(rt.to_host(torch, x))
     seg /= np.max(seg)
     seg[seg < 1e-6] = 0
-    return (seg, {"iterations": iters}) if return_info else seg
+    return (seg, {"iterations": iters, "converged": converged, "last_step": last}) if return_info else seg
 
 
 def calculate_M(kpts_cp, feats_cp, kpts_op, feats_op, F, matches, opts, verbose=False, swap=True, init_ransac=True,

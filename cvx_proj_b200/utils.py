@@ -5,7 +5,11 @@ the canvas is sized from the projected corners of the image to warp (``:99-112``
 with ``cv.warpPerspective`` semantics (bilinear, constant border 0, ``:114``) and the base image is either pasted
 over the result (``direct_blend=True``, ``:124-125``) or mean-blended where the warp left something (``:115-123``,
 the reference's "much slower" Python loop).  Warp and blend are one kernel (``k_warp_global``,
-``csrc/warp_global.cu``), bit-exact with OpenCV's 8-bit fixed-point bilinear warp; the O(1) host arithmetic
+``csrc/warp_global.cu``), bit-exact with OpenCV's 8-bit fixed-point bilinear warp -- the INTER_LINEAR path with
+coordinates in 1/32 pixel and 15-bit weights (``INTER_BITS = 5``, ``INTER_REMAP_COEF_BITS = 15``) that
+``cv.warpPerspective`` takes for ``CV_8UC3``; the golden vectors (``tests/golden/ref_image_warping.npz``) were
+produced with opencv-python 4.13.0, and OpenCV 3.x / 4.x releases share that path (a build that routes 8-bit images
+through a different bilinear kernel would differ by +-1 in some pixels).  The O(1) host arithmetic
 (corner projection, 3x3 inverse) restates ``cv.perspectiveTransform`` / ``cv::invert`` in numpy float64.
 No CPU fallback.
 """

@@ -122,9 +122,10 @@ int apap_local_homography(const float *kp_table, const float *anchors, const dou
 /*
  * Second output of APAP.local_homography (pyviz/apap.py:144,153): float64 weights
  *   out[c][i] = max(exp(-|anchor_c - kp_i| / sigma^2), gamma),  c in [0, cells), i in [0, n_kp)
- *   anchors : double [cells][2];  kp_xy : float [n_kp][2]
+ *   anchors : double [cells][2];  kp_xy : double [n_kp][2] (16-byte aligned; float32 keypoints promoted by the caller,
+ *   which is what numpy does in `vertices[i, j] - src_point`, so float64 keypoints keep their bits too)
  */
-int apap_local_weight(const double *anchors, const float *kp_xy, int cells, int n_kp,
+int apap_local_weight(const double *anchors, const double *kp_xy, int cells, int n_kp,
                       double inv_sigma_sq, double gamma, double *out, void *stream);
 
 /*

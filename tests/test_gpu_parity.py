@@ -962,3 +962,43 @@ def test_peer_copy_writes_every_listed_buffer():
     assert lib.apap_peer_copy(src.data_ptr(), bad, 1, 16, stream) != 0            # misaligned destination
     assert lib.apap_peer_copy(src.data_ptr(), ptrs, 16, 16, stream) != 0           # more than APAP_MAX_PEERS
     assert lib.apap_peer_copy(src.data_ptr(), ptrs, 1, 24, stream) != 0            # size not a multiple of 16
+
+
+def test_spectral_power_iteration_reports_a_repeated_leading_eigenvalue(monkeypatch):
+    """Two disjoint, identical clusters of consistent matches: the affinity matrix is block diagonal with two equal
+    leading eigenvalues, the power iteration cannot settle on one vector -- it must say so (RuntimeWarning,
+    info['converged'] False) instead of returning a mixture silently.  A single cluster converges and says that."""
+    from cvx_proj_b200 import spectral_method as psm
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 50, size=(24, 2)).astype(np.float32)
+    src = np.concatenate([a, a + np.float32(4000.0)])
+    dst = np.concatenate([a + np.float32(3.0), a + np.float32(9000.0)])      # second cluster far away in both images
+    diag = np.full(48, 0.9)
+    monkeypatch.setattr(psm, "POWER_MAX_ITER", 256)
+    with pytest.warns(RuntimeWarning, match="repeated"):
+        _, info = psm.spectral_segment_device(src, dst, diag, 30.0, return_info=True)
+    assert info["converged"] is False and info["iterations"] == 256
+    seg, info = psm.spectral_segment_device(src[:24], dst[:24], diag[:24], 30.0, return_info=True)
+    assert info["converged"] is True and seg.max() == 1.0
+
+
+def test_lazy_local_weight_behaves_like_the_reference_ndarray():
+    """the lazy second return value takes numpy arithmetic, reductions and boolean indexing, keeps
+    float64 keypoints in float64 (the reference subtracts them from float64 vertices), and refuses to build tens of GB
+    in one piece."""
+    sc = synth.make_scene("mini")
+    st = _stitcher(sc)
+    src64 = sc.src.astype(np.float64) + 1e-7                      # not representable in float32
+    _, w = st.local_homography(src64, sc.dst, sc.vertices)
+    want = orc.local_weight(src64, sc.vertices, sc.gamma, sc.sigma)
+    got = np.asarray(w)
+    assert got.shape == want.shape and np.allclose(got, want, rtol=1e-13, atol=0)
+    assert np.allclose(w * 2, want * 2, rtol=1e-13) and np.allclose(2 - w, 2 - want, rtol=1e-12)
+    assert np.isclose(w.sum(), want.sum(), rtol=1e-12) and np.isclose(np.mean(w), want.mean(), rtol=1e-12)
+    assert np.array_equal(w[w > 0.9], got[got > 0.9]) and (w >= sc.gamma).all()
+    assert np.array_equal(np.concatenate([w, w], axis=0), np.concatenate([got, got], axis=0))
+    big = type(w)(sc.src, sc.vertices, sc.gamma, sc.sigma)
+    big.materialize_limit = 1 << 10
+    with pytest.raises(MemoryError):
+        np.asarray(big)
+    assert big[0].shape == want[0].shape                          # slices still stream

@@ -576,3 +576,11 @@ def test_compat_modules_have_the_reference_module_names_and_signatures():
     assert mesh.shape == (2, 5) and mesh.dtype == np.float64
     for name in ("apap", "apap_utils"):
         sys.modules.pop(name, None)
+
+
+def test_cell_lookup_tables_refuse_grids_beyond_16_bit_cell_indices():
+    """the warp tables hold cell rows / columns in 16 bits; a larger grid must not wrap silently."""
+    from cvx_proj_b200.apap import cell_lookup_tables
+    mesh = (np.linspace(0, 100, 70001), np.linspace(0, 100, 11))
+    with pytest.raises(ValueError, match="65535"):
+        cell_lookup_tables(mesh, 100, 100, 10, 70000)
