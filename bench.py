@@ -527,6 +527,8 @@ def run_ours(args):
     if world == 1 and not args.no_extras:
         extras = run_c4_c5(torch, device, flush, mufu_peak * 1e12)
         launches += extras.pop("_launches")
+        extras["matcher"] = run_matcher(torch, device, flush, fp32_peak)
+        launches += extras["matcher"].pop("_launches")
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -646,6 +648,7 @@ def run_ours(args):
     if extras is not None:
         line["c4_batch"] = extras["c4"]
         line["c5_sweep"] = extras["c5"]
+        line["matcher"] = extras["matcher"]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -759,6 +762,46 @@ def run_c3_sharded(torch, dist, device, rank, world, flush, W, K, max_over_ranks
                                       "(N-1)/N of the panorama over NVLink either way",
             "shard": "cell rows + canvas row bands per rank; keypoints and source image replicated",
             "_launches": 5 * K + (3 * K if world > 1 else 0)}
+
+
+def run_matcher(torch, device, flush, fp32_peak):
+    """SURVEY 8f row N3, matcher step: exact 1-NN of 4000 x 4000 SIFT-like descriptors (the c2 keypoint count after
+    border rejection), device-resident and host to host, next to OpenCV's exact and FLANN matchers on this box's CPU."""
+    import time
+    from cvx_proj_b200.utils import match_descriptors
+    rng = np.random.default_rng(0)
+    nq = nt = 4000
+    d = rng.gamma(0.6, 1.0, size=(nt, 128))
+    train = np.minimum(np.rint(d / np.linalg.norm(d, axis=1, keepdims=True) * 512.0), 255.0).astype(np.float32)
+    query = np.clip(train[rng.permutation(nt)] + rng.integers(-6, 7, size=(nq, 128)), 0, 255).astype(np.float32)
+    q_dev, t_dev = torch.from_numpy(query).to(device), torch.from_numpy(train).to(device)
+    ts = []
+    for k in range(8):
+        flush.add_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); match_descriptors(q_dev, t_dev); e1.record(); e1.synchronize()
+        if k >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms_dev = float(np.median(ts))
+    t0 = time.perf_counter()
+    for _ in range(5):
+        match_descriptors(query, train)
+    ms_host = (time.perf_counter() - t0) / 5 * 1e3
+    out = {"what": "exact 1-nearest-neighbour descriptor matching (apap_match_nn) = cv.BFMatcher(NORM_L2).match, bit-identical on "
+                   "SIFT descriptors; the reference calls FLANN's approximate matcher (pyviz/utils.py:149-150)",
+           "queries": nq, "train": nt, "dim": 128, "ms_device": ms_dev, "ms_host_to_host": ms_host,
+           "pairs_per_s": nq * nt / (ms_dev * 1e-3),
+           "fp32_frac": 3.0 * nq * nt * 128 / (ms_dev * 1e-3) / 1e12 / fp32_peak,
+           "fp32_note": "3 flop (subtract, multiply, add) per component of a (query, train) pair on the packed FP32x2 pipe, "
+                        "against the FFMA probe peak of this run", "_launches": 13 * 3}
+    try:
+        import cv2 as cv
+        t0 = time.perf_counter(); cv.BFMatcher(cv.NORM_L2).match(query, train); ms_bf = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); cv.FlannBasedMatcher().match(query, train); ms_flann = (time.perf_counter() - t0) * 1e3
+        out["cpu"] = {"cv_bfmatcher_ms": ms_bf, "cv_flann_ms": ms_flann, "threads": cv.getNumThreads()}
+    except ImportError:
+        out["cpu"] = None
+    return out
 
 
 def run_c4_c5(torch, device, flush, mufu_peak):

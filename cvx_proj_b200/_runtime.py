@@ -19,7 +19,7 @@ KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
 WARP_BLOCK_ROWS = 4
-ABI_VERSION = 20
+ABI_VERSION = 21
 KP_BLOCK = 8
 KP_BLOCK_FLOATS = 528
 GRAM_TCGEN05 = 0
@@ -58,6 +58,7 @@ SIGNATURES = {
     "apap_power_iterate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "apap_multicast_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "apap_peer_copy": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
+    "apap_match_nn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apap_invert_grid": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "apap_kp_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
     "apap_condition": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

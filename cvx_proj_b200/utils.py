@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _runtime as rt
 
-__all__ = ["image_warping", "warp_perspective", "warping_canvas", "invert3x3"]
+__all__ = ["image_warping", "warp_perspective", "warping_canvas", "invert3x3", "match_descriptors", "coarse_matching"]
 
 
 def invert3x3(m) -> np.ndarray:
@@ -96,3 +96,55 @@ def image_warping(img_base, img2warp, H, direct_blend=True, device=None):
     cw, ch, tx, ty, m = warping_canvas(img_base.shape, img2warp.shape, H)
     return warp_perspective(img2warp, m, (cw, ch), base=img_base, offset=(tx, ty), mode=1 if direct_blend else 2,
                             device=device)
+
+
+# ------------------------------------------------------------------ keypoint-pair producer
+def match_descriptors(feats_query, feats_train, device=None):
+    """Exact 1-nearest-neighbour match of every query descriptor in the train set on the GPU (``apap_match_nn``):
+    ``(train_idx int32 [nq], distance float32 [nq])`` = what ``cv.BFMatcher(cv.NORM_L2).match(feats_query, feats_train)``
+    returns as ``DMatch.trainIdx`` / ``.distance`` -- bit for bit for integer-valued descriptors such as SIFT's.
+    The reference calls ``cv.FlannBasedMatcher().match`` (pyviz/utils.py:149-150), an approximate search whose result
+    changes from run to run; the exact neighbour is what it approximates.  Arrays or CUDA tensors ``[n, dim]`` float32,
+    ``dim`` even and <= 256."""
+    torch, device = rt.torch_cuda(device if device is not None else (feats_query.device if hasattr(feats_query, "device") and
+                                                                    not isinstance(feats_query, np.ndarray) else None))
+    lib = rt.load_library()
+
+    def dev(a):
+        if isinstance(a, np.ndarray):
+            return rt.to_device(torch, device, np.ascontiguousarray(a, dtype=np.float32))
+        if a.dtype != torch.float32:
+            raise TypeError("device descriptors must be float32 tensors")
+        return a.contiguous()
+    host_out = isinstance(feats_query, np.ndarray)
+    q, t = dev(feats_query), dev(feats_train)
+    if q.dim() != 2 or t.dim() != 2 or (t.shape[0] and q.shape[1] != t.shape[1]):
+        raise ValueError("match_descriptors: descriptors are [n, dim] arrays of one dim")
+    nq, nt, dim = int(q.shape[0]), int(t.shape[0]), int(q.shape[1])
+    idx = torch.empty(nq, dtype=torch.int32, device=device)
+    dist = torch.empty(nq, dtype=torch.float32, device=device)
+    scratch = torch.empty(max(nq, 1), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        rt.check(lib.apap_match_nn(q.data_ptr(), t.data_ptr() if nt else None, nq, nt, dim, scratch.data_ptr(),
+                                   idx.data_ptr(), dist.data_ptr(), rt.stream_ptr(torch, device)), "apap_match_nn")
+    if host_out:
+        return rt.to_host(torch, idx), rt.to_host(torch, dist)
+    return idx, dist
+
+
+def coarse_matching(c_img, o_img, raw_kpts_cp, raw_kpts_op, device=None):
+    """``coarse_matching`` of the reference (pyviz/utils.py:142-151) -- same arguments, same return tuple
+    ``(kpts_cp, feats_cp, kpts_op, feats_op, matches)`` with ``matches`` a list of ``cv.DMatch`` (one per centre
+    keypoint, in query order).  SIFT descriptors at the given keypoints are OpenCV's own (``cv.SIFT.compute``, host:
+    un-vendored, no bit-level restatement exists); the matcher is the exact nearest neighbour on the GPU
+    (``match_descriptors``) where the reference asks FLANN's randomised kd-trees for an approximation of it."""
+    import cv2 as cv
+
+    kpts_cp = [cv.KeyPoint(*pt, 1) for pt in raw_kpts_cp]
+    kpts_op = [cv.KeyPoint(*pt, 1) for pt in raw_kpts_op]
+    extractor = cv.SIFT.create(nfeatures=128)
+    kpts_cp, feats_cp = extractor.compute(c_img, kpts_cp)
+    kpts_op, feats_op = extractor.compute(o_img, kpts_op)
+    idx, dist = match_descriptors(feats_cp, feats_op, device=device)
+    matches = [cv.DMatch(i, int(j), 0, float(d)) for i, (j, d) in enumerate(zip(idx, dist)) if j >= 0]
+    return kpts_cp, feats_cp, kpts_op, feats_op, matches

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 20
+#define APAP_ABI_VERSION 21
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -308,6 +308,18 @@ int apap_affinity_matrix(const float *src_pts, const float *dst_pts, const doubl
                          double *m, void *stream);
 int apap_power_iterate(const double *m, int n, double *y, double *norms, int first_step, int steps, double *x,
                        unsigned long long *max_diff_bits, void *stream);
+
+/*
+ * Exact 1-nearest-neighbour descriptor matching: the matcher step of the reference's keypoint-pair producer,
+ * cv.FlannBasedMatcher().match(feats_cp, feats_op) (pyviz/utils.py:149-150).  FLANN is approximate
+ * and not reproducible, so the contract is cv.BFMatcher(cv.NORM_L2).match on the same descriptors: per query the train
+ * index with the smallest sum_k (q_k - t_k)^2 (float32; the lowest index on a tie) and distance = sqrt of that sum --
+ * bit-identical to OpenCV for integer-valued descriptors (SIFT: 0..255), equal up to float32 near-ties otherwise.
+ *   query : float [nq][dim], train : float [nt][dim] (device, 8-byte aligned; dim even, <= 256)
+ *   scratch : uint64 [nq] (device);  idx : out int32 [nq] (-1 when nt == 0);  dist : out float [nq]
+ */
+int apap_match_nn(const float *query, const float *train, int nq, int nt, int dim, unsigned long long *scratch,
+                  int *idx, float *dist, void *stream);
 
 /*
  * Panorama assembly of a sharded pass without an all-gather: broadcast `bytes` of device memory at `src` (this

@@ -1002,3 +1002,88 @@ def test_lazy_local_weight_behaves_like_the_reference_ndarray():
     with pytest.raises(MemoryError):
         np.asarray(big)
     assert big[0].shape == want[0].shape                          # slices still stream
+
+
+# ------------------------------------------------------------- keypoint-pair producer: matcher
+def _sift_like(rng, n, dim=128):
+    """Integer-valued float32 descriptors with SIFT's range and norm (0..255, L2 norm ~512)."""
+    d = rng.gamma(0.6, 1.0, size=(n, dim))
+    d = d / np.linalg.norm(d, axis=1, keepdims=True) * 512.0
+    return np.minimum(np.rint(d), 255.0).astype(np.float32)
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (5, 3), (64, 32), (65, 33), (381, 381), (3975, 4100), (300, 20000)])
+def test_exact_matcher_equals_cv_bfmatcher(nq, nt):
+    """apap_match_nn against the live cv.BFMatcher(NORM_L2).match and the numpy oracle on SIFT-like descriptors: same
+    train index and the same float32 distance bits for every query, duplicates in the train set included (a tie
+    falls to the lowest train index, as in OpenCV)."""
+    import cv2 as cv
+    from cvx_proj_b200.utils import match_descriptors
+    from oracle import match_oracle as mo
+    rng = np.random.default_rng(nq * 7 + nt)
+    train = _sift_like(rng, nt)
+    noise = rng.integers(-6, 7, size=(nq, 128)).astype(np.float32)
+    query = np.clip(train[rng.integers(0, nt, size=nq)] + noise, 0, 255).astype(np.float32)
+    if nt >= 8:
+        train[nt // 2] = train[1]                                  # an exact duplicate: ties
+        query[0] = train[1]
+    idx, dist = match_descriptors(query, train)
+    want_idx, want_dist = mo.exact_match(query, train)
+    assert np.array_equal(idx, want_idx) and np.array_equal(dist.view(np.uint32), want_dist.view(np.uint32))
+    bf = cv.BFMatcher(cv.NORM_L2).match(query, train)
+    assert len(bf) == nq
+    assert np.array_equal(idx, np.array([m.trainIdx for m in bf], dtype=np.int32))
+    assert np.array_equal(dist.view(np.uint32), np.array([m.distance for m in bf], dtype=np.float32).view(np.uint32))
+    if nt >= 8:
+        assert idx[0] == 1 and dist[0] == 0.0
+
+
+def test_exact_matcher_edge_cases_and_general_floats():
+    """Empty sets, other descriptor widths, CUDA tensors in / out, and non-integer descriptors: the index is the exact
+    nearest neighbour wherever the two smallest distances differ by more than float32 rounding."""
+    import torch
+    from cvx_proj_b200.utils import match_descriptors
+    from oracle import match_oracle as mo
+    rng = np.random.default_rng(0)
+    idx, dist = match_descriptors(np.zeros((0, 128), np.float32), _sift_like(rng, 10))
+    assert idx.shape == (0,) and dist.shape == (0,)
+    idx, dist = match_descriptors(_sift_like(rng, 7), np.zeros((0, 128), np.float32))
+    assert (idx == -1).all() and np.isinf(dist).all()
+    for dim in (2, 64, 130, 256):
+        q, t = rng.standard_normal((97, dim)).astype(np.float32), rng.standard_normal((211, dim)).astype(np.float32)
+        idx, dist = match_descriptors(q, t)
+        d2 = ((q[:, None, :].astype(np.float64) - t[None].astype(np.float64)) ** 2).sum(-1)
+        order = np.sort(d2, axis=1)
+        clear = order[:, 1] - order[:, 0] > 1e-5 * order[:, 1]
+        assert clear.mean() > 0.9 and np.array_equal(idx[clear], d2.argmin(1)[clear])
+        assert np.allclose(dist, np.sqrt(d2[np.arange(97), idx]), rtol=1e-5)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    q, t = _sift_like(rng, 130), _sift_like(rng, 70)
+    idx_d, dist_d = match_descriptors(torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev))
+    assert idx_d.is_cuda and np.array_equal(idx_d.cpu().numpy(), mo.exact_match(q, t)[0])
+    with pytest.raises(rt.ApapError):
+        match_descriptors(np.zeros((3, 7), np.float32), np.zeros((3, 7), np.float32))       # odd width
+
+
+def test_coarse_matching_mirror_on_a_synthetic_pair():
+    """cvx_proj_b200.utils.coarse_matching (pyviz/utils.py:142-151): OpenCV's own SIFT descriptors at the given keypoints,
+    matches = the exact nearest neighbours; on a pair related by a known homography nearly all of them are the true
+    correspondences, and cv.findHomography on them (the reference's next call, baseline_stitch_test.py:40) recovers it."""
+    import cv2 as cv
+    from cvx_proj_b200.utils import coarse_matching
+    sc = synth.make_scene("c1")
+    img_c = synth.make_image(sc.width, sc.height, seed=2)
+    hinv = np.linalg.inv(sc.h_gt)
+    img_o = cv.warpPerspective(img_c, hinv, (sc.width, sc.height))
+    raw_c = sc.dst.astype(np.float32)
+    raw_o = cv.perspectiveTransform(raw_c[None].astype(np.float64), hinv)[0].astype(np.float32)
+    keep = np.all((raw_o > 16) & (raw_o < [sc.width - 16, sc.height - 16]) & (raw_c > 16) & (raw_c < [sc.width - 16, sc.height - 16]), axis=1)
+    raw_c, raw_o = raw_c[keep], raw_o[keep]
+    kc, fc, ko, fo, matches = coarse_matching(img_c, img_o, raw_c, raw_o)
+    assert len(matches) == len(kc) == fc.shape[0] and all(isinstance(m, cv.DMatch) for m in matches)
+    bf = cv.BFMatcher(cv.NORM_L2).match(fc, fo)
+    assert [m.trainIdx for m in matches] == [m.trainIdx for m in bf]
+    assert np.mean([m.trainIdx == m.queryIdx for m in matches]) > 0.8
+    src = np.float32([kc[m.queryIdx].pt for m in matches]); dst = np.float32([ko[m.trainIdx].pt for m in matches])
+    h, mask = cv.findHomography(src, dst, cv.RANSAC, 5.0)
+    assert mask.sum() > 0.8 * len(matches) and np.abs(h / h[2, 2] - hinv / hinv[2, 2]).max() < 0.05 * np.abs(hinv / hinv[2, 2]).max()

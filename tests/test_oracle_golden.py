@@ -158,3 +158,20 @@ def test_spectral_oracle_reproduces_live_reference(golden):
         assert np.array_equal(seg, g[name + "_segment"])
         assert np.array_equal(rmask, g[name + "_ransac_mask"]) and np.array_equal(omask, g[name + "_original_mask"])
     assert set(CASES) == {"s40", "s300", "s1000", "s2500"}
+
+
+def test_match_oracle_equals_live_bfmatcher():
+    """oracle/match_oracle.exact_match is pinned against OpenCV's own exact matcher (the dependency the reference's
+    matcher step lives in): same train index and distance bits on SIFT-like integer descriptors, ties included."""
+    cv = pytest.importorskip("cv2")
+    from oracle import match_oracle as mo
+    rng = np.random.default_rng(5)
+    for nq, nt in ((1, 1), (40, 17), (300, 900)):
+        t = np.minimum(np.rint(rng.gamma(0.6, 40.0, size=(nt, 128))), 255).astype(np.float32)
+        q = np.clip(t[rng.integers(0, nt, size=nq)] + rng.integers(-5, 6, size=(nq, 128)), 0, 255).astype(np.float32)
+        if nt > 4:
+            t[nt - 1] = t[2]; q[0] = t[2]
+        idx, dist = mo.exact_match(q, t)
+        bf = cv.BFMatcher(cv.NORM_L2).match(q, t)
+        assert np.array_equal(idx, [m.trainIdx for m in bf])
+        assert np.array_equal(dist.view(np.uint32), np.array([m.distance for m in bf], np.float32).view(np.uint32))
