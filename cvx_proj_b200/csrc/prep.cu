@@ -465,11 +465,13 @@ __global__ void __launch_bounds__(512) k_weight_bound(const float2 *__restrict__
   src_raw += (size_t)scene * n_points;
   anchors += (size_t)scene * cells;
   float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  for (int i = tid; i < n; i += 512) {
+#pragma unroll 8
+  for (int i = tid; i < n; i += 512) {             // unrolled: eight loads in flight per thread (one CTA covers a scene)
     const float2 v = src_raw[i];
     lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
     lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
   }
+#pragma unroll 8
   for (int i = tid; i < cells; i += 512) {
     const float2 v = anchors[i];
     lo[2] = fminf(lo[2], v.x); hi[2] = fmaxf(hi[2], v.x);
