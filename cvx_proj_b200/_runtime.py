@@ -19,7 +19,7 @@ KP_ROW = 28
 KP_CHUNK = 128
 HINV_ROW = 12
 WARP_BLOCK_ROWS = 4
-ABI_VERSION = 21
+ABI_VERSION = 22
 KP_BLOCK = 8
 KP_BLOCK_FLOATS = 528
 GRAM_TCGEN05 = 0
@@ -41,6 +41,9 @@ SIGNATURES = {
     "apap_eig_denorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "apap_local_homography": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "apap_pass_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "apap_local_homography_points": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_float,
+                                             c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "apap_local_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     "apap_warp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int, c_int,

@@ -693,23 +693,6 @@ class APAP:
         table = build_kp_table(src_point.astype(np.float32, copy=False), dlt, weight_scale(self.sigma))
         return table, tmats
 
-    def _upload_scene(self, torch, device, points, counts, anchors):
-        """One host->device copy for all kernel inputs of ``batch`` scenes: the arrays are packed into a pinned
-        staging buffer (kept per instance) and sliced on the device.
-        Layout: float32 points [2, b, n, 2] (raw source, raw target) | int32 counts [b] | float32 anchors [b, cells, 2]
-        (every section starts 16-byte aligned).  The O(N) prologue of pyviz/apap.py:129-141 then runs on the device
-        (``apap_condition``).  Returns the keypoint ROW table built from the points on the device, the anchors, the
-        de-normalisation matrices, the per-scene weight bound (``weight_bound_device``)."""
-        if not hasattr(self, "_stage"):
-            self._stage = _PinnedStage()
-        p_u8, c_u8, a_u8 = self._stage.upload(torch, device, (points, counts, anchors))
-        raw = p_u8.view(torch.float32).view(points.shape)
-        counts_dev = c_u8.view(torch.int32)
-        cond, tmats = self.condition_device(raw, counts_dev)
-        rows = self.kp_rows_device((cond[0], cond[1], raw[0]), counts_dev)
-        anchors_dev = a_u8.view(torch.float32).view(anchors.shape)
-        return rows, anchors_dev, tmats, self.weight_bound_device(raw[0], counts_dev, anchors_dev)
-
     def weight_bound_device(self, raw_src_dev, counts_dev, anchors_dev):
         """``apap_weight_bound``: per scene an upper bound of the pre-scaled distance of pyviz/apap.py:150-151 over all
         (cell, match) pairs -- K1 leaves the clamp of :152 out for a scene where it cannot trigger (same bits).
@@ -830,17 +813,57 @@ class APAP:
         mesh_n, pt_size, _ = np.shape(vertices)
         if sample_n == 0:
             raise ValueError("local_homography needs at least one match")
-        torch, device = rt.torch_cuda(self.device)
-        cells = mesh_n * pt_size
-        anchors = scale_anchors(vertices, weight_scale(self.sigma))
         points = np.empty((2, 1, sample_n, 2), dtype=np.float32)
         points[0, 0], points[1, 0] = src_point, dst_point
-        counts = np.array([sample_n], dtype=np.int32)
-        t_dev, a_dev, m_dev, bound = self._upload_scene(torch, device, points, counts, anchors[None])
-        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, 1, cells, t_bound=bound)
-        h = rt.to_host(torch, h_dev).reshape(mesh_n, pt_size, 3, 3)
+        verts = np.ascontiguousarray(vertices, dtype=np.float64).reshape(1, mesh_n * pt_size, 2)
+        h = self._homography_pass(points, None, verts).reshape(mesh_n, pt_size, 3, 3)
         weight = LazyLocalWeight(np.asarray(src_point), np.asarray(vertices), self.gamma, self.sigma, self.device)
         return h, weight
+
+    def _homography_pass(self, points, counts, verts):
+        """Raw inputs up, ONE library call (``apap_local_homography_points``: anchors, conditioning, keypoint table,
+        clamp bound, K1, K2), H down.  ``points`` float32 ``[2, b, n, 2]`` (source, target), ``counts`` int32 ``[b]`` or
+        None, ``verts`` float64 ``[b, cells, 2]``.  Returns H ``[b, cells, 9]`` float32 (host).  The device scratch is
+        kept per shape; big inputs that already sit in pinned memory go up without the staging copy."""
+        torch, device = rt.torch_cuda(self.device)
+        lib = rt.load_library()
+        _, batch, n, _ = points.shape
+        cells = verts.shape[1]
+        engine = rt.GRAM_TCGEN05 if self.gram_engine == "tcgen05" else rt.GRAM_FFMA2
+        key = (str(device), batch, n, cells, engine)
+        ws = getattr(self, "_pass_ws", None)
+        if ws is None or ws[0] != key:
+            import ctypes
+            need = ctypes.c_size_t()
+            rt.check(lib.apap_pass_workspace_bytes(batch, n, cells, engine, ctypes.byref(need)), "apap_pass_workspace_bytes")
+            ws = (key, torch.empty(int(need.value), dtype=torch.uint8, device=device))
+            self._pass_ws = ws
+        if not hasattr(self, "_stage"):
+            self._stage = _PinnedStage()
+        small = [points] + ([counts] if counts is not None else [])
+        v_t = torch.from_numpy(verts)
+        if v_t.is_pinned():                              # no staging copy for what is already pinned
+            parts = self._stage.upload(torch, device, small)
+            v_dev = v_t.to(device, non_blocking=True)
+        else:
+            parts = self._stage.upload(torch, device, small + [verts])
+            v_dev = parts[-1]
+        p_dev = parts[0]
+        c_dev = parts[1] if counts is not None else None
+        out_h = torch.empty((batch, cells, 9), dtype=torch.float32, device=device)
+        counters = self._tile_counters(torch, device, batch, cells) if engine == rt.GRAM_TCGEN05 else None
+        half = batch * n * 8                             # bytes of one point set
+        try:
+            with torch.cuda.device(device):
+                rt.check(lib.apap_local_homography_points(
+                    p_dev.data_ptr(), p_dev.data_ptr() + half, c_dev.data_ptr() if c_dev is not None else None, batch, n,
+                    v_dev.data_ptr(), cells, weight_scale(self.sigma), float(np.float32(float(self.gamma) ** 2)), engine,
+                    rt.EIG_AUTO, ws[1].data_ptr(), ws[1].numel(), counters.data_ptr() if counters is not None else None,
+                    out_h.data_ptr(), None, rt.stream_ptr(torch, device)), "apap_local_homography_points")
+        except Exception:
+            self._counters = None          # a failed call may leave counts behind: never reuse that scratch
+            raise
+        return rt.to_host(torch, out_h)
 
     def local_homography_batch(self, src_points, dst_points, vertices):
         """Extension (no reference API; its multi-image mode is a shell loop, run_all.sh:15,29):
@@ -856,11 +879,8 @@ class APAP:
         points = np.zeros((2, count, int(counts.max()), 2), dtype=np.float32)
         for k, (s, d) in enumerate(zip(src_points, dst_points)):
             points[0, k, :counts[k]], points[1, k, :counts[k]] = s, d
-        anchors = np.stack([scale_anchors(v, weight_scale(self.sigma)) for v in verts])
-        torch, device = rt.torch_cuda(self.device)
-        t_dev, a_dev, m_dev, bound = self._upload_scene(torch, device, points, counts, anchors)
-        h_dev = self.local_homography_device(self.kp_table_device(t_dev), a_dev, m_dev, count, cells, t_bound=bound)
-        h = rt.to_host(torch, h_dev).reshape(count, mesh_n, pt_size, 3, 3)
+        stacked = np.stack([np.asarray(v, dtype=np.float64).reshape(cells, 2) for v in verts])
+        h = self._homography_pass(points, counts, stacked).reshape(count, mesh_n, pt_size, 3, 3)
         return [h[k] for k in range(count)]
 
     # ---- mesh warp -----------------------------------------------------------------------------

@@ -508,6 +508,39 @@ int launch_weight_bound(const float *src_raw, const int *counts, int batch, int 
   return check_cuda(cudaGetLastError(), "k_weight_bound launch");
 }
 
+// ------------------------------------------------------------------------------------ k_scale_anchors
+// anchors = float32(vertices * s): numpy's `(vertices * scale).astype(np.float32)` (apap.scale_anchors), on the device
+__global__ void __launch_bounds__(256) k_scale_anchors(const double *__restrict__ v, size_t n, double scale,
+                                                       float *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = __double2float_rn(__dmul_rn(v[i], scale));
+}
+
+// The device buffers of one whole local_homography call (apap_local_homography_points), in one workspace
+struct PassLayout {
+  size_t cond, mats, tmats, anchors, bound, rows, blocks, partials, total;
+  int n_pad;
+};
+
+static PassLayout pass_layout(int batch, int n_points, int cells, int engine) {
+  PassLayout l;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off = (off + bytes + 255) / 256 * 256; return at; };
+  l.n_pad = (n_points + kChunk - 1) / kChunk * kChunk;
+  if (l.n_pad < kChunk) l.n_pad = kChunk;
+  const GramPlan p = make_gram_plan(cells, l.n_pad, engine);
+  l.cond = take((size_t)2 * batch * n_points * 2 * sizeof(float));
+  l.mats = take((size_t)batch * 36 * sizeof(float));
+  l.tmats = take((size_t)batch * 18 * sizeof(double));
+  l.anchors = take((size_t)batch * cells * 2 * sizeof(float));
+  l.bound = take((size_t)batch * sizeof(float));
+  l.rows = take((size_t)batch * l.n_pad * kRowFloats * sizeof(float));
+  l.blocks = take(engine == APAP_GRAM_TCGEN05 ? (size_t)batch * (l.n_pad / APAP_KP_BLOCK) * APAP_KP_BLOCK_FLOATS * sizeof(float) : 0);
+  l.partials = take((size_t)batch * p.k_splits * kTerms * p.cells_padded * sizeof(float));
+  l.total = off;
+  return l;
+}
+
 }  // namespace apap
 
 using namespace apap;
@@ -550,6 +583,49 @@ int apap_kp_blocks(const float *kp_table, int batch, int n_kp_padded, float *kp_
   if (!kp_table || !kp_blocks) return fail(APAP_E_BADARG, "null pointer");
   if (batch <= 0 || n_kp_padded <= 0 || n_kp_padded % kChunk) return fail(APAP_E_BADARG, "kp_blocks: bad sizes");
   return launch_kp_blocks(kp_table, batch, n_kp_padded, kp_blocks, static_cast<cudaStream_t>(stream));
+}
+
+int apap_pass_workspace_bytes(int batch, int n_points, int cells, int engine, size_t *bytes) {
+  if (!bytes) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || n_points <= 0 || cells <= 0) return fail(APAP_E_BADARG, "pass workspace: bad sizes");
+  if (engine != APAP_GRAM_TCGEN05 && engine != APAP_GRAM_FFMA2) return fail(APAP_E_BADARG, "pass workspace: unknown engine");
+  *bytes = pass_layout(batch, n_points, cells, engine).total;
+  return 0;
+}
+
+int apap_local_homography_points(const float *src, const float *dst, const int *counts, int batch, int n_points,
+                                 const double *vertices, int cells, double scale, float gamma_sq, int engine, int solver,
+                                 void *workspace, size_t workspace_bytes, int *tile_counters, float *out_h,
+                                 int *out_sweeps, void *stream) {
+  if (!src || !dst || !vertices || !workspace || !out_h) return fail(APAP_E_BADARG, "null pointer");
+  if (batch <= 0 || n_points <= 0 || cells <= 0) return fail(APAP_E_BADARG, "local_homography_points: bad sizes");
+  if (engine != APAP_GRAM_TCGEN05 && engine != APAP_GRAM_FFMA2) return fail(APAP_E_BADARG, "local_homography_points: unknown engine");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) || (reinterpret_cast<uintptr_t>(vertices) & 7u))
+    return fail(APAP_E_ALIGN, "local_homography_points: workspace must be 256-byte aligned, vertices 8-byte aligned");
+  const PassLayout l = pass_layout(batch, n_points, cells, engine);
+  if (workspace_bytes < l.total) return fail(APAP_E_BADARG, "local_homography_points: workspace smaller than apap_pass_workspace_bytes");
+  char *ws = static_cast<char *>(workspace);
+  float *cond = reinterpret_cast<float *>(ws + l.cond), *mats = reinterpret_cast<float *>(ws + l.mats);
+  double *tmats = reinterpret_cast<double *>(ws + l.tmats);
+  float *anchors = reinterpret_cast<float *>(ws + l.anchors), *bound = reinterpret_cast<float *>(ws + l.bound);
+  float *rows = reinterpret_cast<float *>(ws + l.rows), *blocks = reinterpret_cast<float *>(ws + l.blocks);
+  float *partials = reinterpret_cast<float *>(ws + l.partials);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n_anchor = (size_t)batch * cells * 2;
+  k_scale_anchors<<<(unsigned)((n_anchor + 255) / 256), 256, 0, st>>>(vertices, n_anchor, scale, anchors);
+  int rc = check_cuda(cudaGetLastError(), "k_scale_anchors launch");
+  if (rc) return rc;
+  if ((rc = apap_condition(src, dst, counts, batch, n_points, cond, mats, tmats, stream))) return rc;
+  const float *cf1 = cond, *cf2 = cond + (size_t)batch * n_points * 2;
+  if ((rc = apap_kp_rows(cf1, cf2, src, counts, batch, n_points, l.n_pad, scale, rows, stream))) return rc;
+  if ((rc = apap_weight_bound(src, counts, batch, n_points, scale, anchors, cells, bound, stream))) return rc;
+  const float *table = rows;
+  if (engine == APAP_GRAM_TCGEN05) {
+    if ((rc = apap_kp_blocks(rows, batch, l.n_pad, blocks, stream))) return rc;
+    table = blocks;
+  }
+  return apap_local_homography(table, anchors, tmats, batch, cells, l.n_pad, gamma_sq, engine, solver, bound, partials,
+                               tile_counters, out_h, out_sweeps, stream);
 }
 
 int apap_invert_grid(const float *grid, int cells, float *grid_inv, unsigned char *flags, void *stream) {

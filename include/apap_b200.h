@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APAP_ABI_VERSION 21
+#define APAP_ABI_VERSION 22
 
 /* Layout constants shared with the host layer. */
 #define APAP_GRAM_TERMS 24   /* distinct non-zero sums of the 9x9 Gram matrix (4 sym. 3x3 blocks) */
@@ -118,6 +118,22 @@ int apap_local_homography(const float *kp_table, const float *anchors, const dou
                           int batch, int cells, int n_kp_padded, float gamma_sq, int engine, int solver,
                           const float *t_bound, float *partials, int *tile_counters, float *out_h, int *out_sweeps,
                           void *stream);
+
+/*
+ * The whole of APAP.local_homography (pyviz/apap.py:121-169) in ONE call, from the raw inputs as the caller has them:
+ * anchors = float32(vertices * scale), apap_condition, apap_kp_rows, apap_weight_bound, apap_kp_blocks (engine TCGEN05),
+ * then apap_local_homography -- the same kernels in the same order as the separate entry points (same bits), without a
+ * host round trip between them.  What the Python class calls.
+ *   src, dst  : float [batch][n_points][2] raw matched points;  counts : int32 [batch] or NULL
+ *   vertices  : double [batch][cells][2] = get_vertice's anchor points, unscaled;  scale = s = 2 log2(e) / sigma^2
+ *   workspace : device scratch, 256-byte aligned, >= apap_pass_workspace_bytes(batch, n_points, cells, engine)
+ *   tile_counters, out_h, out_sweeps : as in apap_local_homography
+ */
+int apap_pass_workspace_bytes(int batch, int n_points, int cells, int engine, size_t *bytes);
+int apap_local_homography_points(const float *src, const float *dst, const int *counts, int batch, int n_points,
+                                 const double *vertices, int cells, double scale, float gamma_sq, int engine, int solver,
+                                 void *workspace, size_t workspace_bytes, int *tile_counters, float *out_h,
+                                 int *out_sweeps, void *stream);
 
 /*
  * Second output of APAP.local_homography (pyviz/apap.py:144,153): float64 weights

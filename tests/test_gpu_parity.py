@@ -1087,3 +1087,33 @@ def test_coarse_matching_mirror_on_a_synthetic_pair():
     src = np.float32([kc[m.queryIdx].pt for m in matches]); dst = np.float32([ko[m.trainIdx].pt for m in matches])
     h, mask = cv.findHomography(src, dst, cv.RANSAC, 5.0)
     assert mask.sum() > 0.8 * len(matches) and np.abs(h / h[2, 2] - hinv / hinv[2, 2]).max() < 0.05 * np.abs(hinv / hinv[2, 2]).max()
+
+
+def test_one_call_pass_equals_the_separate_entry_points():
+    """apap_local_homography_points (what APAP.local_homography calls: anchors scaled, conditioned, tabled, bounded and
+    solved by ONE library call) gives the same H bits as the separate entry points driven from Python, for a single
+    pair, a ragged batch, both engines, and with pinned or pageable vertices."""
+    import torch
+    from cvx_proj_b200.apap import scale_anchors, weight_scale
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for engine in ENGINES:
+        sc = synth.make_scene("c1")
+        st = _stitcher(sc, engine=engine)
+        h, _ = st.local_homography(sc.src, sc.dst, sc.vertices)
+        vert_pin = rt.pinned_empty(sc.vertices.shape, np.float64); vert_pin[...] = sc.vertices
+        h_pin, _ = st.local_homography(sc.src, sc.dst, vert_pin)
+        raw = torch.from_numpy(np.stack([sc.src, sc.dst]).astype(np.float32)[:, None]).to(dev)
+        cond, tmats = st.condition_device(raw)
+        rows = st.kp_rows_device((cond[0], cond[1], raw[0]))
+        a = torch.from_numpy(scale_anchors(sc.vertices, weight_scale(sc.sigma))[None]).to(dev)
+        bound = st.weight_bound_device(raw[0], None, a)
+        want = st.local_homography_device(st.kp_table_device(rows), a, tmats, 1, sc.n_cells, t_bound=bound).cpu().numpy()
+        assert np.array_equal(h.reshape(-1, 9).view(np.uint32), want.reshape(-1, 9).view(np.uint32))
+        assert np.array_equal(h.view(np.uint32), h_pin.view(np.uint32))
+        # ragged batch: every item equals its single-pair call
+        scs = [synth.make_scene("mini", seed=k, n_kp=n) for k, n in enumerate((200, 131, 77))]
+        stb = _stitcher(scs[0], engine=engine)
+        got = stb.local_homography_batch([s.src for s in scs], [s.dst for s in scs], [s.vertices for s in scs])
+        for s_, g in zip(scs, got):
+            one, _ = stb.local_homography(s_.src, s_.dst, s_.vertices)
+            assert np.array_equal(g.view(np.uint32), one.view(np.uint32))

@@ -297,7 +297,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(rt.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.apap_abi_version() == rt.ABI_VERSION == 21
+    assert lib.apap_abi_version() == rt.ABI_VERSION == 22
     m = re.search(r"#define\s+APAP_KP_ROW\s+(\d+)", header)
     assert int(m.group(1)) == rt.KP_ROW
 
