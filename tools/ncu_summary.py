@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` report of tools/profile_pass.py into profiles/:
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep c2 r01
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep c2 r01 [--append]
 
 writes profiles/<round>_ncu_summary.md (one block per kernel: duration, DRAM traffic, registers,
 issue / pipe utilisation, top stall reasons) and updates profiles/ncu_traffic.json
@@ -47,6 +47,7 @@ def short(name):
 
 def main():
     rep, workload, rnd = sys.argv[1], sys.argv[2], sys.argv[3]
+    append = len(sys.argv) > 4 and sys.argv[4] == "--append"     # a second capture (more kernels) of the same round
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
@@ -75,13 +76,16 @@ def main():
         traffic[name] = int(dram)
     os.makedirs(os.path.join(REPO, "profiles"), exist_ok=True)
     md = os.path.join(REPO, "profiles", f"{rnd}_ncu_summary.md")
-    with open(md, "w") as f:
-        f.write(f"# ncu --set full --clock-control none, `tools/profile_pass.py {workload}` ({os.path.basename(rep)})\n\n"
+    with open(md, "a" if append else "w") as f:
+        f.write(("\n" if append else "") + f"# ncu --set full --clock-control none, `tools/profile_pass.py {workload}` ({os.path.basename(rep)})\n\n"
                 "Per-launch values of the first captured launch of each kernel (cold caches, serialised by the "
                 "profiler: compare shares, not absolutes).\n\n" + "\n".join(out) + "\n")
     tj = os.path.join(REPO, "profiles", "ncu_traffic.json")
     allt = json.load(open(tj)) if os.path.exists(tj) else {}
-    allt[workload] = traffic                       # the capture replaces the workload's table: no stale kernels of older rounds
+    if append:
+        allt.setdefault(workload, {}).update(traffic)
+    else:
+        allt[workload] = traffic                   # the capture replaces the workload's table: no stale kernels of older rounds
     with open(tj, "w") as f:
         json.dump(allt, f, indent=1, sort_keys=True)
     print("wrote", md, "and", tj, traffic)

@@ -21,6 +21,9 @@ import numpy as np  # noqa: E402
 
 sp_o, sp_c, _h = synth.make_keypoints(1024, 768, 2500, seed=11)
 sp_diag = np.full(2500, 0.95)
+_rng = np.random.default_rng(0)
+mq = torch.from_numpy(np.rint(_rng.uniform(0, 255, (4000, 128))).astype(np.float32)).to(dev)
+mt = torch.from_numpy(np.rint(_rng.uniform(0, 255, (4000, 128))).astype(np.float32)).to(dev)
 
 g_cw, g_ch, g_tx, g_ty, g_m = putils.warping_canvas(p.host_img.shape, p.host_img.shape, p.sc.h_gt)
 g_out = torch.empty((g_ch, g_cw, 3), dtype=torch.uint8, device=dev)
@@ -42,6 +45,9 @@ for _ in range(iters):
     p.warp(False); p.warp(True); p.blend()
     gw(0); gw(1); gw(2)                                 # k_warp_global: warp only, paste, mean blend
     if _ == 0:
+        from cvx_proj_b200.utils import match_descriptors
+        match_descriptors(mq, mt)                       # k_match_nn, k_match_finish
+        p.st.local_homography(p.sc.src, p.sc.dst, p.sc.vertices)   # the one-call chain (k_scale_anchors first)
         psm.spectral_segment_device(sp_c, sp_o, sp_diag, 30.0, device=dev)   # k_affinity, k_power_step, k_power_diff
 torch.cuda.synchronize()
 print("profile pass ok", name, iters)
