@@ -24,10 +24,11 @@ constexpr int kMaxChainChunks = APAP_MAX_CHAIN_CHUNKS;   // FFMA2 engine: 8 x 12
 // The tensor-core engine never runs an FP32 chain longer than a 256-keypoint segment (its splits only exist for
 // parallelism), so its splits may be longer: fewer partial planes for K2 to read (c3: 311 -> 156 MB).
 #ifndef APAP_MAX_SPLIT_CHUNKS_TC
-#define APAP_MAX_SPLIT_CHUNKS_TC 32
+#define APAP_MAX_SPLIT_CHUNKS_TC 16
 #endif
-constexpr int kMaxSplitChunksTc = APAP_MAX_SPLIT_CHUNKS_TC;   // 32 x 128 = 4096 keypoints per split (c3: K1 the same, K2 reads half
-                                                            // the planes: 63 -> 45 us, partials 156 -> 78 MB; H moves by 6e-7 of the gate's scale)
+constexpr int kMaxSplitChunksTc = APAP_MAX_SPLIT_CHUNKS_TC;   // 16 x 128 = 2048 keypoints per split.  32 (4096) was measured in round 2:
+// c3 on one GPU 1.734 -> 1.709 ms (K2 reads half the planes), but an eighth of c3 is then 1.8 waves of CTAs instead of 3.5
+// and the 8-GPU shard goes from 0.251 to 0.270 ms -- the plan is a function of N only, so the sharded case decides
 
 struct GramPlan {
   int k_splits;
