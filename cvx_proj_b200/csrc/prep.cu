@@ -457,7 +457,8 @@ int launch_inv_grid(const float *h, int cells, float *out, unsigned char *flags,
 // ------------------------------------------------------------------------------------ k_weight_bound
 // t_bound[scene] >= |s v - s x| for every (anchor v, keypoint x) of the scene: the diagonal of the two sets' bounding
 // boxes taken together.  K1 drops the clamp max(w, gamma^2) for a scene whose bound shows that no weight reaches it.
-__global__ void __launch_bounds__(512) k_weight_bound(const float2 *__restrict__ src_raw, const int *__restrict__ counts,
+constexpr int kBoundThreads = 1024;   // one CTA per scene: 40 000 anchors are 39 loads per thread, eight in flight
+__global__ void __launch_bounds__(kBoundThreads) k_weight_bound(const float2 *__restrict__ src_raw, const int *__restrict__ counts,
                                                       int n_points, double scale, const float2 *__restrict__ anchors,
                                                       int cells, float *__restrict__ t_bound) {
   const int scene = blockIdx.x, tid = threadIdx.x;
@@ -466,18 +467,18 @@ __global__ void __launch_bounds__(512) k_weight_bound(const float2 *__restrict__
   anchors += (size_t)scene * cells;
   float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 8
-  for (int i = tid; i < n; i += 512) {             // unrolled: eight loads in flight per thread (one CTA covers a scene)
+  for (int i = tid; i < n; i += kBoundThreads) {             // unrolled: eight loads in flight per thread (one CTA covers a scene)
     const float2 v = src_raw[i];
     lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
     lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
   }
 #pragma unroll 8
-  for (int i = tid; i < cells; i += 512) {
+  for (int i = tid; i < cells; i += kBoundThreads) {
     const float2 v = anchors[i];
     lo[2] = fminf(lo[2], v.x); hi[2] = fmaxf(hi[2], v.x);
     lo[3] = fminf(lo[3], v.y); hi[3] = fmaxf(hi[3], v.y);
   }
-  __shared__ float red[2][4][16];
+  __shared__ float red[2][4][kBoundThreads / 32];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(512) k_weight_bound(const float2 *__restrict__
   if (tid == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      for (int w = 1; w < 16; ++w) { lo[k] = fminf(lo[0 + k], red[0][k][w]); hi[k] = fmaxf(hi[k], red[1][k][w]); }
+      for (int w = 1; w < kBoundThreads / 32; ++w) { lo[k] = fminf(lo[0 + k], red[0][k][w]); hi[k] = fmaxf(hi[k], red[1][k][w]); }
     // keypoints go into the table as float(s * x): the same product here, in double, then the widest gap per axis
     const double kx0 = scale * lo[0], kx1 = scale * hi[0], ky0 = scale * lo[1], ky1 = scale * hi[1];
     const double dx = fmax(fabs(kx1 - lo[2]), fabs(hi[2] - kx0)), dy = fmax(fabs(ky1 - lo[3]), fabs(hi[3] - ky0));
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(512) k_weight_bound(const float2 *__restrict__
 
 int launch_weight_bound(const float *src_raw, const int *counts, int batch, int n_points, double scale,
                         const float *anchors, int cells, float *t_bound, cudaStream_t st) {
-  k_weight_bound<<<batch, 512, 0, st>>>(reinterpret_cast<const float2 *>(src_raw), counts, n_points, scale,
+  k_weight_bound<<<batch, kBoundThreads, 0, st>>>(reinterpret_cast<const float2 *>(src_raw), counts, n_points, scale,
                                         reinterpret_cast<const float2 *>(anchors), cells, t_bound);
   return check_cuda(cudaGetLastError(), "k_weight_bound launch");
 }
