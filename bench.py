@@ -517,7 +517,7 @@ def run_ours(args):
     e2e_warp_s = max_over_ranks(float(np.mean(e2e_warp)))
     h2d_dlt = 2 * sc.src.shape[0] * 8 + p.cells * 16              # raw source and target points (float32), anchor points (float64)
     d2h_dlt = p.cells * 36
-    h2d_warp = 3 * src_px + 2 * p.cells * 36 + 8 * sc.final_w + 8 * p.tables.n_blocks + 16 * sc.mesh_cells   # grid up twice: to invert, inverted
+    h2d_warp = 3 * src_px + p.cells * 36 + 8 * sc.final_w + 8 * p.tables.n_blocks + 16 * sc.mesh_cells   # image, grid (inverted on the device), LUTs
     d2h_warp = 3 * canvas_px + p.cells * 37                      # canvas + the inverted grid and its flags
 
     # ---- c3 strong-scaled across ranks (cell rows + row bands, one all-gather) -----------------
@@ -625,7 +625,7 @@ def run_ours(args):
             "e2e": {"value": world * canvas_px / e2e_warp_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_warp,
                     "d2h_bytes_per_step": d2h_warp, "ms_per_step": e2e_warp_s * 1e3,
                     "call": "APAP.local_warp(img, H, mesh) with a pinned numpy image, numpy canvas out "
-                            "(includes the in-place per-cell inverse of pyviz/apap.py:201-203: certified GPU inverse, numpy for the cells it flags)"},
+                            "(includes the in-place per-cell inverse of pyviz/apap.py:201-203: certified GPU inverse kept on the device for the warp and copied back into the caller's array, numpy for the cells it flags)"},
             "exact_path_cells_frac": p.flagged_cells,
         },
         "global_warp": {

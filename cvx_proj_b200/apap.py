@@ -893,10 +893,11 @@ class APAP:
             self._lut_cache = {key: hit}
         return hit
 
-    def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None, row0=0, row1=None):
+    def warp_tables_device(self, inv_h, col_cell, row_cell, src_w, src_h, device=None, row0=0, row1=None, hinv_dev=None):
         """The warp kernel's inputs for an inverted grid and the canvas rows ``[row0, row1)``: one
         host->device copy (inverted grid, column LUT, row blocks, cell extents), then the per-cell
-        fast-path records are built on the device (``apap_warp_tables``)."""
+        fast-path records are built on the device (``apap_warp_tables``).  ``hinv_dev``: the inverted grid as a float32
+        device tensor ``[cells * 9]`` (``inv_h`` is then only read for its shape and not uploaded)."""
         torch, device = rt.torch_cuda(device if device is not None else self.device)
         lib = rt.load_library()
         row1 = int(self.final_height) if row1 is None else row1
@@ -909,11 +910,14 @@ class APAP:
             hit = (key, col_lut, blocks, col_ext, row_ext)
             self._warp_lut_cache = hit
         _, col_lut, blocks, col_ext, row_ext = hit
-        hinv = np.ascontiguousarray(inv_h, dtype=np.float32).reshape(-1, 9)
         if not hasattr(self, "_warp_stage"):
             self._warp_stage = _PinnedStage()
-        views = self._warp_stage.upload(torch, device, (hinv, col_lut, blocks, col_ext, row_ext))
-        hinv_dev = views[0].view(torch.float32)
+        if hinv_dev is None:
+            hinv = np.ascontiguousarray(inv_h, dtype=np.float32).reshape(-1, 9)
+            views = self._warp_stage.upload(torch, device, (hinv, col_lut, blocks, col_ext, row_ext))
+            hinv_dev = views[0].view(torch.float32)
+        else:
+            views = [None] + self._warp_stage.upload(torch, device, (col_lut, blocks, col_ext, row_ext))
         fast = torch.empty(gr * gc * HINV_ROW, dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             rt.check(lib.apap_warp_tables(hinv_dev.data_ptr(), views[3].data_ptr(), views[4].data_ptr(), gr, gc,
@@ -974,24 +978,49 @@ class APAP:
         ``np.linalg.inv`` itself here, so errors surface exactly as in the reference (``LinAlgError``).
         Returns the number of cells numpy inverted.  Grids that are not C-contiguous float32 take numpy throughout."""
         grid = local_homography
-        if not (isinstance(grid, np.ndarray) and grid.dtype == np.float32 and grid.flags.c_contiguous
-                and grid.ndim >= 2 and grid.shape[-2:] == (3, 3)) or grid.size == 0:
+        if not self._gpu_invertible(grid):
             invert_grid_inplace(grid)
             return int(grid.size // 9)
         torch, device = rt.torch_cuda(device if device is not None else self.device)
+        _, out_pin, flag_pin, _ = self._invert_grid_async(torch, device, grid)
+        torch.cuda.current_stream(device).synchronize()
+        return self._invert_grid_finish(grid, out_pin, flag_pin)
+
+    @staticmethod
+    def _gpu_invertible(grid) -> bool:
+        return (isinstance(grid, np.ndarray) and grid.dtype == np.float32 and grid.flags.c_contiguous
+                and grid.ndim >= 2 and grid.shape[-2:] == (3, 3) and grid.size > 0)
+
+    def _invert_grid_async(self, torch, device, grid):
+        """Enqueue upload, ``apap_invert_grid`` and the copies back (pinned) without waiting: ``(inverse on the device
+        float32 [cells * 9], pinned host inverse, pinned host flags, event after the flags copy)``; the host arrays are
+        valid once the stream (the flags: the event) has been waited for."""
         lib = rt.load_library()
         cells = grid.size // 9
-        flat = grid.reshape(cells, 3, 3)
         with torch.cuda.device(device):
             g_dev = rt.to_device(torch, device, grid)
             out_dev = torch.empty(cells * 9, dtype=torch.float32, device=device)
             flag_dev = torch.empty(cells, dtype=torch.uint8, device=device)
             rt.check(lib.apap_invert_grid(g_dev.data_ptr(), cells, out_dev.data_ptr(), flag_dev.data_ptr(),
                                           rt.stream_ptr(torch, device)), "apap_invert_grid")
-            out = rt.to_host(torch, out_dev)
-            redo = np.flatnonzero(rt.to_host(torch, flag_dev))
-        fixed = np.linalg.inv(flat[redo]) if redo.size else None      # before anything is overwritten; may raise
-        flat[...] = out.reshape(cells, 3, 3)
+            out_pin = torch.empty(cells * 9, dtype=torch.float32, pin_memory=True)
+            flag_pin = torch.empty(cells, dtype=torch.uint8, pin_memory=True)
+            flag_pin.copy_(flag_dev, non_blocking=True)
+            flags_here = torch.cuda.Event()
+            flags_here.record()                          # the host may read the flags once this has passed
+            out_pin.copy_(out_dev, non_blocking=True)
+        return out_dev, out_pin, flag_pin, flags_here
+
+    @staticmethod
+    def _invert_grid_finish(grid, out_pin, flag_pin, redo=None, fixed=None):
+        """Store the inverses into the caller's array (the cells the GPU could not certify through ``np.linalg.inv``,
+        which may raise like the reference -- before anything is overwritten).  Returns the number of cells redone."""
+        cells = grid.size // 9
+        flat = grid.reshape(cells, 3, 3)
+        if redo is None:
+            redo = np.flatnonzero(flag_pin.numpy())
+            fixed = np.linalg.inv(flat[redo]) if redo.size else None
+        flat[...] = out_pin.numpy().reshape(cells, 3, 3)
         if redo.size:
             flat[redo] = fixed
         return int(redo.size)
@@ -1005,21 +1034,49 @@ class APAP:
         ori_h, ori_w, _ = ori_img.shape
         on_device = not isinstance(ori_img, np.ndarray)
         torch, device = rt.torch_cuda(ori_img.device if on_device else self.device)
-        # the image copies go first: they are asynchronous from pinned memory
+        col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
+        gpu_inverse = self._gpu_invertible(local_homography)
+        # the grid goes up first (1.4 MB), is inverted, and its flags come back while the image copies -- asynchronous
+        # from pinned memory -- are still in flight behind them: waiting for the flags costs nothing
+        if gpu_inverse:
+            hinv_dev, out_pin, flag_pin, flags_here = self._invert_grid_async(torch, device, local_homography)
         src_dev = ori_img.contiguous() if on_device else rt.to_device(torch, device, ori_img.astype(np.uint8, copy=False))
         centre_dev = None
         if centre_img is not None:
             centre_dev = (centre_img.contiguous() if not isinstance(centre_img, np.ndarray)
                           else rt.to_device(torch, device, centre_img.astype(np.uint8, copy=False)))
+
+        def run(hinv_dev):
+            tables = self.warp_tables_device(local_homography, col_cell, row_cell, ori_w, ori_h, device, hinv_dev=hinv_dev)
+            if interpolation == "bilinear":
+                return self.warp_bilinear_device(src_dev, tables, pt_size)
+            return self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)
+
         # in-place per-cell inverse, stored back in the caller's array (pyviz/apap.py:201-203)
-        self.invert_grid(local_homography, device)
-        col_cell, row_cell = self._luts(mesh, mesh_n, pt_size)
-        tables = self.warp_tables_device(local_homography, col_cell, row_cell, ori_w, ori_h, device)
-        if interpolation == "bilinear":
-            out = self.warp_bilinear_device(src_dev, tables, pt_size)
-        else:
-            out = self.warp_device(src_dev, tables, pt_size, centre_dev=centre_dev, force_exact=force_exact)
-        return out if on_device else rt.to_host(torch, out)
+        if not gpu_inverse:
+            self.invert_grid(local_homography, device)
+            out = run(None)
+            return out if on_device else rt.to_host(torch, out)
+        flags_here.synchronize()
+        cells = mesh_n * pt_size
+        redo = np.flatnonzero(flag_pin.numpy())
+        fixed = None
+        if redo.size:
+            # the cells the certificate turned down: numpy's own inverse (raises like the reference, nothing has been
+            # overwritten yet), patched into the device copy the warp reads
+            fixed = np.linalg.inv(local_homography.reshape(cells, 3, 3)[redo])
+            with torch.cuda.device(device):
+                idx = torch.from_numpy(redo.astype(np.int64)).to(device)
+                vals = torch.from_numpy(np.ascontiguousarray(fixed, dtype=np.float32).reshape(-1, 9)).to(device)
+                hinv_dev.view(cells, 9).index_copy_(0, idx, vals)
+        out = run(hinv_dev)
+        host = None
+        if not on_device:
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        self._invert_grid_finish(local_homography, out_pin, flag_pin, redo, fixed)
+        return out if on_device else host.numpy()
 
     def warp_bilinear_device(self, src_dev, tables, grid_cols, out=None):
         """Device-resident opt-in bilinear mode (``apap_warp_bilinear``): the canvas rows ``[tables.row0, tables.row1)``."""
