@@ -584,3 +584,52 @@ def test_cell_lookup_tables_refuse_grids_beyond_16_bit_cell_indices():
     mesh = (np.linspace(0, 100, 70001), np.linspace(0, 100, 11))
     with pytest.raises(ValueError, match="65535"):
         cell_lookup_tables(mesh, 100, 100, 10, 70000)
+
+
+def test_pass_workspace_layout_is_host_side_and_consistent():
+    """apap_pass_workspace_bytes (the scratch of the one-call apap_local_homography_points) is pure host arithmetic:
+    it answers without a GPU, grows with every dimension, covers the partial planes of the gram plan, and rejects
+    nonsense."""
+    import ctypes
+    lib = rt.load_library()
+
+    def need(batch, n, cells, engine):
+        out = ctypes.c_size_t()
+        rc = lib.apap_pass_workspace_bytes(batch, n, cells, engine, ctypes.byref(out))
+        return rc, int(out.value)
+
+    for engine in (rt.GRAM_TCGEN05, rt.GRAM_FFMA2):
+        rc, base = need(1, 5000, 40_000, engine)
+        assert rc == 0 and base % 256 == 0
+        n_pad = 5120
+        _, _, partial = rt.gram_plan(40_000, n_pad, engine)
+        rows = n_pad * 28 * 4
+        blocks = (n_pad // 8) * 528 * 4 if engine == rt.GRAM_TCGEN05 else 0
+        assert base >= partial + rows + blocks + 40_000 * 8 + 2 * 5000 * 8
+        assert base < 1.05 * (partial + rows + blocks + 40_000 * 8 + 2 * 5000 * 8) + 8 * 256
+        assert need(2, 5000, 40_000, engine)[1] > base
+        assert need(1, 5200, 40_000, engine)[1] > base            # one more chunk of keypoints
+        assert need(1, 5000, 41_000, engine)[1] > base
+    assert need(0, 10, 10, 0)[0] != 0 and need(1, 0, 10, 0)[0] != 0 and need(1, 10, 10, 7)[0] != 0
+
+
+def test_invert_grid_finish_writes_numpys_inverse_for_flagged_cells():
+    """The host tail of the device inverse (APAP._invert_grid_finish): certified cells take the device's bits, flagged
+    cells numpy's own inverse computed from the caller's values BEFORE anything is overwritten; a singular flagged cell
+    raises like np.linalg.inv and leaves the array untouched."""
+    import torch
+    rng = np.random.default_rng(2)
+    grid = (np.eye(3) + 0.1 * rng.standard_normal((6, 3, 3))).astype(np.float32)
+    before = grid.copy()
+    device_inverse = torch.from_numpy(np.linalg.inv(before).reshape(-1) + np.float32(1.0))     # recognisably "the GPU's"
+    flags = torch.tensor([0, 1, 0, 0, 1, 0], dtype=torch.uint8)
+    assert papap.APAP._invert_grid_finish(grid, device_inverse, flags) == 2
+    want = device_inverse.numpy().reshape(6, 3, 3).copy()
+    want[[1, 4]] = np.linalg.inv(before[[1, 4]])
+    assert np.array_equal(grid, want)
+    singular = before.copy()
+    singular[4] = 0
+    keep = singular.copy()
+    with pytest.raises(np.linalg.LinAlgError):
+        papap.APAP._invert_grid_finish(singular, device_inverse, flags)
+    assert np.array_equal(singular, keep)
